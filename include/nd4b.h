@@ -1,0 +1,138 @@
+/* nd4b.h — C ABI of libnd4b.so: the B200 (sm_100a) implementation of nd4js's broadcast-batched
+ * Float64 dense linear-algebra hot path.
+ *
+ * The reference (nd4js v1.3.0) has no FFI layer: call sites import plain JS functions.  The
+ * drop-in boundary is therefore "the JS function body": a JS shim with the reference's names and
+ * signatures keeps asarray()/shape inference/error texts in JS and hands flat Float64Array /
+ * Int32Array buffers to an N-API addon that binds exactly the entry points below
+ * (see INTEGRATION.md for the shim and the addon).  Each entry point cites the reference
+ * function it replaces (paths relative to the nd4js checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all matrices dense, row-major, batch-major (src/nd_array.js:128-147)
+ *   - return 0 on success, <0 argument errors (same codes as the texts the reference throws),
+ *     >0 numerical failure; nd4b_last_error() returns the reference's message text (thread-local)
+ *   - "host" entry points take HOST pointers (pinned or pageable), block until the results are in
+ *     the caller's buffers, never write to inputs, retain nothing; work is sharded over the
+ *     context's devices by contiguous ranges of the flattened leading batch index
+ *   - "dev" entry points take DEVICE pointers valid on `device`, enqueue on `stream`
+ *     (a cudaStream_t passed as void*) and return without synchronising
+ *   - there is NO CPU fallback: every entry point fails with ND4B_E_CUDA if no device is usable
+ */
+#ifndef ND4B_H
+#define ND4B_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ND4B_OK             0
+#define ND4B_E_A_NDIM     (-1)  /* 'A must be at least 2D.'                         src/la/matmul.js:95   */
+#define ND4B_E_B_NDIM     (-2)  /* 'B must be at least 2D.'                         src/la/matmul.js:96   */
+#define ND4B_E_INNER      (-3)  /* 'The last dimension of A and the 2nd to last dimension of B do not match.' :101-102 */
+#define ND4B_E_BROADCAST  (-4)  /* 'Shapes are not broadcast-compatible.'           src/la/matmul.js:116  */
+#define ND4B_E_SHAPE      (-5)  /* result shape passed by the caller is not the broadcast shape           */
+#define ND4B_E_NOT_SQUARE (-6)  /* 'Last two dimensions must be quadratic.'         src/la/cholesky.js:61 */
+#define ND4B_E_NAN_INPUT  (-7)  /* 'Assertion failed.' (KahanSum.set on NaN)        src/kahan_sum.js:29   */
+#define ND4B_E_ARG        (-8)  /* null pointer / non-positive dimension (NDArray rejects dims < 1, src/nd_array.js:138) */
+#define ND4B_E_CUDA       (-9)  /* CUDA runtime failure or no usable device; text in nd4b_last_error()     */
+#define ND4B_E_NO_CONVERGENCE (-10) /* Jacobi SVD hit the sweep limit (NaN/Inf input)                     */
+#define ND4B_E_SINGULAR     1   /* 'Matrix contains NaNs or is (near) singular.'    src/la/cholesky.js:44 */
+
+#define ND4B_MAX_NDIM 32
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Creates the process-wide context on the given CUDA device ordinals (NULL/0: the ND4B_DEVICES
+ * environment variable, e.g. "0,1,2,3", else the current device).  Idempotent for an equal list. */
+int nd4b_init(const int* devices, int n_devices);
+int nd4b_shutdown(void);
+int nd4b_device_count(void);            /* devices in the context (0 before init)            */
+const char* nd4b_last_error(void);      /* message of the last failing call on this thread   */
+const char* nd4b_version(void);
+
+/* Page-locked host memory, so a caller (the N-API addon creates external ArrayBuffers from it)
+ * can keep Float64Array storage DMA-able and skip the staging copy. */
+void* nd4b_host_alloc(size_t bytes);
+void nd4b_host_free(void* p);
+
+/* Bytes of pipeline chunk per device stream (default 32 MiB); also ND4B_CHUNK_MB in the environment. */
+int nd4b_set_chunk_bytes(size_t bytes);
+
+typedef struct nd4b_stats {
+  uint64_t calls;            /* host entry-point calls                      */
+  uint64_t kernel_launches;  /* kernels launched by this library            */
+  uint64_t h2d_bytes;        /* bytes copied host -> device                 */
+  uint64_t d2h_bytes;        /* bytes copied device -> host                 */
+  uint64_t staged_bytes;     /* bytes that went through the pinned ring     */
+  int32_t last_sweeps;       /* Jacobi sweeps of the last svd call (max over batch) */
+  int32_t n_devices;
+} nd4b_stats;
+int nd4b_get_stats(nd4b_stats* out);
+int nd4b_reset_stats(void);
+
+/* ---- nd.la.matmul2 — src/la/matmul.js:91-147 (shape rules) + :31-74 (matmul2_RR) ------------- */
+
+/* Broadcast result shape of matmul2(a,b); c_shape must hold max(a_ndim,b_ndim) entries. */
+int nd4b_matmul_shape(const int32_t* a_shape, int a_ndim, const int32_t* b_shape, int b_ndim,
+                      int32_t* c_shape, int* c_ndim);
+
+/* C[...,I,J] = A[...,I,K] . B[...,K,J] with NumPy-style broadcasting of the leading dims. */
+int nd4b_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
+                    const double* B, const int32_t* b_shape, int b_ndim,
+                    double* C, const int32_t* c_shape, int c_ndim);
+
+/* ---- nd.la.cholesky_decomp — src/la/cholesky.js:50-72, _cholesky_decomp :27-47 --------------- */
+
+/* Reads only the lower triangle of every S; L's strict upper triangle is +0.  On ND4B_E_SINGULAR
+ * *first_bad is the flattened batch index of the first failing matrix (reference: the exception
+ * aborts the whole call), L is then unspecified. */
+int nd4b_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t* first_bad);
+
+/* ---- nd.la.qr_decomp — src/la/qr.js:80-145 (and :27-77 for rows <= cols) --------------------- */
+
+/* Q[batch,rows,min(rows,cols)], R[batch,min(rows,cols),cols]; R exactly upper triangular with
+ * diag(R) >= 0 (the reference's Givens QR leaves arbitrary signs on diag(R): compare sign-normalised). */
+int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols);
+
+/* ---- nd.la.svd_jac_1sided — contract of the svd_jac_* family, src/la/svd_jac_2sided.js:30-144,
+ *      ordering/sign rules src/la/_svd_jac_utils.js:123-188, shapes src/help.js:2321-2337 ------- */
+
+/* U[batch,rows,L], sv[batch,L] (descending, >= +0), V[batch,L,cols], L=min(rows,cols),
+ * A = U diag(sv) V.  *sweeps_out (may be NULL): max Jacobi sweeps over the batch. */
+int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
+                      int64_t batch, int rows, int cols, int* sweeps_out);
+
+/* ---- device-resident forms (inputs already in HBM; used for composition and kernel timing) --- */
+
+/* Batched C[m] = A[m*a_stride] . B[m*b_stride]; strides in ELEMENTS between consecutive matrices,
+ * 0 broadcasts the operand (the whole-operand case of matmul.js:59-67). */
+int nd4b_dev_matmul_f64(int device, void* stream, const double* A, int64_t a_stride,
+                        const double* B, int64_t b_stride, double* C,
+                        int64_t batch, int I, int K, int J);
+/* info (device int64, may be NULL): min batch index whose factorisation failed, else INT64_MAX;
+ * the caller initialises it. */
+int nd4b_dev_cholesky_f64(int device, void* stream, const double* S, double* L,
+                          int64_t batch, int n, long long* info);
+int nd4b_dev_qr_f64(int device, void* stream, const double* A, double* Q, double* R,
+                    int64_t batch, int rows, int cols, double* workspace, size_t workspace_bytes);
+/* sweeps (device int32, may be NULL): atomicMax of sweeps used.  workspace as reported below. */
+int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, double* sv, double* V,
+                          int64_t batch, int rows, int cols, int* sweeps,
+                          double* workspace, size_t workspace_bytes);
+/* Scratch bytes the dev_qr / dev_svd forms need for this problem (0 for the specialised shapes). */
+size_t nd4b_dev_qr_workspace(int64_t batch, int rows, int cols);
+size_t nd4b_dev_svd_workspace(int64_t batch, int rows, int cols);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+
+/* Times one launch of an FP64 pipe probe on `device` (which: 0 = DFMA vector pipe, 16 chains x 2 flop x iters
+ * per thread; 1 = DMMA.8x8x4 tensor pipe, 8 tiles x 512 flop x iters per warp).  Used to measure the FP64
+ * roofline denominators that MEASURED_PEAKS.json lacks. */
+int nd4b_probe_fp64(int device, int which, int iters, int blocks, int threads, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

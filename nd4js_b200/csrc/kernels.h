@@ -1,0 +1,43 @@
+// kernels.h — host-side launch interface of the nd4b CUDA kernels (internal; the public ABI is include/nd4b.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace nd4b {
+
+// Broadcast odometer of matmul2 (nd4js src/la/matmul.js:44-70) in closed form: the flattened batch
+// index m of C is decomposed over size[0..nd) (row-major) and mapped to operand element offsets by
+// per-dim strides; a stride of 0 repeats the operand along that dim (dim is 1 or absent).
+struct BatchMap {
+  int nd;             // number of (collapsed) leading dims used by the odometer, 0..8
+  int64_t base;       // global batch index of the first matrix of this launch (sharding / chunking)
+  int64_t a_lin;      // >= 0: operand A is addressed linearly, offset = local_index * a_lin (0 = one matrix for all)
+  int64_t b_lin;      //  < 0: operand is resident as a whole and addressed through the odometer with the global index
+  int64_t size[8];
+  int64_t a_str[8];
+  int64_t b_str[8];
+};
+
+cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, double* C,
+                          int64_t batch, int I, int K, int J, const BatchMap& map, int sm_count);
+
+// info: device int64, atomicMin of (base_index + m) over matrices whose factorisation produced a NaN pivot.
+cudaError_t launch_cholesky(cudaStream_t s, const double* S, double* L, int64_t batch, int n,
+                            long long* info, long long base_index);
+
+size_t qr_workspace_bytes(int64_t batch, int rows, int cols);
+cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols,
+                      double* work, size_t work_bytes);
+
+size_t svd_workspace_bytes(int64_t batch, int rows, int cols);
+// sweeps: device int32 (atomicMax).  fail: device int32 set to 1 if some matrix hit the sweep limit.
+cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* sv, double* V,
+                            int64_t batch, int rows, int cols, int* sweeps, int* fail,
+                            double* work, size_t work_bytes);
+
+// fp64 peak probes (tools/ and bench use them to measure the FP64 roofline denominators)
+cudaError_t launch_probe_dfma(cudaStream_t s, double* out, int iters, int blocks, int threads);
+cudaError_t launch_probe_dmma(cudaStream_t s, double* out, int iters, int blocks, int threads);
+
+}  // namespace nd4b

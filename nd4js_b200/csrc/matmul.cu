@@ -1,0 +1,295 @@
+// matmul.cu — broadcast-batched fp64 GEMM kernels (replaces matmul2_RR, nd4js src/la/matmul.js:31-74).
+//
+// Two kernels:
+//  * matmul32_kernel     : I=K=J=32, one warp per matrix triple, operands loaded straight from HBM
+//                          into DMMA fragment registers with 16-byte loads.  HBM-bound
+//                          (24 576 B and 65 536 flop per matrix, AI 2.67 flop/B).
+//  * gemm_tiled_kernel   : any I,K,J; CTA tile in padded shared memory, DMMA.8x8x4 from smem.
+// The reference accumulates each C_ij sequentially in k with separately rounded mul and add; the
+// tensor-core path accumulates with fused multiply-adds in a different k order, so results agree
+// componentwise to a few ulp of (|A||B|)_ij (tests/ state the bound), not bit for bit.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nd4b {
+
+__device__ __forceinline__ void decode_batch(const BatchMap& map, int64_t m_local, int64_t& ao, int64_t& bo) {
+  ao = m_local * map.a_lin;
+  bo = m_local * map.b_lin;
+  if (map.a_lin >= 0 && map.b_lin >= 0) return;
+  int64_t m = m_local + map.base, oa = 0, ob = 0;
+#pragma unroll 1
+  for (int d = map.nd - 1; d >= 0; d--) {
+    const int64_t q = m / map.size[d];
+    const int64_t idx = m - q * map.size[d];
+    oa += idx * map.a_str[d];
+    ob += idx * map.b_str[d];
+    m = q;
+  }
+  if (map.a_lin < 0) ao = oa;
+  if (map.b_lin < 0) bo = ob;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 32x32x32, warp per matrix.
+//
+// lane = 4g+t.  k is consumed in the order k(w,h,t) = 8w+2t+h so that thread t's two A values of
+// k-steps (w,0),(w,1) are one 16-byte load; tile columns are n(x,e,g) = 16x+e+2g so that a thread's
+// two B values of tiles (x,0),(x,1) are one 16-byte load and its four C values of (x,0),(x,1) are
+// 32 contiguous bytes.  Permuting k and n inside an MMA is free (same permutation on both operands /
+// on B and C).  Per warp instruction: A load 8 rows x 64 B, B load 4 rows x 128 B, C store 8 rows x 64 B.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMM32Warps = 8;
+
+__global__ void __launch_bounds__(kMM32Warps * 32)
+matmul32_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                int64_t batch, BatchMap map) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t m = (int64_t)blockIdx.x * kMM32Warps + warp;
+  if (m >= batch) return;
+  int64_t ao, bo;
+  decode_batch(map, m, ao, bo);
+  const double* a = A + ao + g * 32 + 2 * t;
+  const double* b = B + bo + (2 * t) * 32 + 2 * g;
+  double* c = C + m * 1024 + g * 32 + 4 * t;
+
+  double2 bf[4][2][2];
+#pragma unroll
+  for (int w = 0; w < 4; w++)
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int x = 0; x < 2; x++) bf[w][h][x] = ldg2(b + (8 * w + h) * 32 + 16 * x);
+
+  double2 af[4][4];
+#pragma unroll
+  for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+    for (int w = 0; w < 4; w++) af[rb][w] = ldg2(a + rb * 256 + 8 * w);
+
+#pragma unroll
+  for (int rb = 0; rb < 4; rb++) {
+    double acc[2][2][2];
+#pragma unroll
+    for (int x = 0; x < 2; x++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) acc[x][e][0] = acc[x][e][1] = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double av = h ? af[rb][w].y : af[rb][w].x;
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+          dmma884(acc[x][0][0], acc[x][0][1], av, bf[w][h][x].x);
+          dmma884(acc[x][1][0], acc[x][1][1], av, bf[w][h][x].y);
+        }
+      }
+#pragma unroll
+    for (int x = 0; x < 2; x++) {
+      double* p = c + rb * 256 + 16 * x;
+      stg2_stream(p, acc[x][0][0], acc[x][1][0]);
+      stg2_stream(p + 2, acc[x][0][1], acc[x][1][1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// General tiled GEMM.  CTA = WR x WC warps, each warp owns a (8*TM) x (8*TN) block of C.
+// smem tiles are padded so that DMMA fragment reads (8 rows x 4 k, resp. 4 k x 8 cols of doubles)
+// hit 16 distinct 8-byte bank pairs per half warp:  row stride == 4 (mod 16) doubles.
+// ------------------------------------------------------------------------------------------------
+template <int WR, int WC, int TM, int TN>
+struct TileCfg {
+  static constexpr int BM = WR * TM * 8, BN = WC * TN * 8, BK = 16;
+  static constexpr int LDA = BK + 4;  // 20 doubles
+  static constexpr int LDB = BN + 4;  // == 4 mod 16 because BN is a multiple of 16
+  static constexpr int THREADS = WR * WC * 32;
+  static constexpr int A_ELEMS = BM * BK, B_ELEMS = BK * BN;
+  static constexpr int A_PER_THR = A_ELEMS / THREADS, B_PER_THR = B_ELEMS / THREADS;
+  static_assert(BN % 16 == 0, "BN must be a multiple of 16");
+  static_assert(A_ELEMS % (2 * THREADS) == 0 && B_ELEMS % (2 * THREADS) == 0, "tile/threads mismatch");
+};
+
+template <int WR, int WC, int TM, int TN, bool VEC>
+__global__ void __launch_bounds__(WR * WC * 32)
+gemm_tiled_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                  int64_t batch, int I, int K, int J, BatchMap map, int tiles_m, int tiles_n) {
+  using Cfg = TileCfg<WR, WC, TM, TN>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB;
+  constexpr int T = Cfg::THREADS;
+  __shared__ __align__(16) double As[2][BM * LDA];
+  __shared__ __align__(16) double Bs[2][BK * LDB];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp / WC, wc = warp % WC;
+
+  int64_t tile = blockIdx.x;
+  const int tn = (int)(tile % tiles_n); tile /= tiles_n;
+  const int tm = (int)(tile % tiles_m); tile /= tiles_m;
+  const int64_t m = tile;
+  if (m >= batch) return;
+  int64_t ao, bo;
+  decode_batch(map, m, ao, bo);
+  const double* a = A + ao;
+  const double* b = B + bo;
+  double* c = C + m * (int64_t)I * J;
+  const int row0 = tm * BM, col0 = tn * BN;
+
+  // global -> register staging.  VEC: 16-byte loads (requires K,J even and 16-byte aligned bases).
+  constexpr int AV = VEC ? Cfg::A_PER_THR / 2 : Cfg::A_PER_THR;
+  constexpr int BV = VEC ? Cfg::B_PER_THR / 2 : Cfg::B_PER_THR;
+  double ra[Cfg::A_PER_THR], rb[Cfg::B_PER_THR];
+
+  auto load_tiles = [&](int k0) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < AV; i++) {
+        const int e = (tid + i * T) * 2, r = e / BK, kk = e % BK;
+        const int gr = row0 + r, gk = k0 + kk;
+        double2 v = make_double2(0.0, 0.0);
+        if (gr < I && gk < K) v = ldg2(a + (int64_t)gr * K + gk);  // K even => gk+1 < K
+        ra[2 * i] = v.x; ra[2 * i + 1] = v.y;
+      }
+#pragma unroll
+      for (int i = 0; i < BV; i++) {
+        const int e = (tid + i * T) * 2, kk = e / BN, cc = e % BN;
+        const int gk = k0 + kk, gc = col0 + cc;
+        double2 v = make_double2(0.0, 0.0);
+        if (gk < K && gc < J) v = ldg2(b + (int64_t)gk * J + gc);
+        rb[2 * i] = v.x; rb[2 * i + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < AV; i++) {
+        const int e = tid + i * T, r = e / BK, kk = e % BK;
+        const int gr = row0 + r, gk = k0 + kk;
+        ra[i] = (gr < I && gk < K) ? __ldg(a + (int64_t)gr * K + gk) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < BV; i++) {
+        const int e = tid + i * T, kk = e / BN, cc = e % BN;
+        const int gk = k0 + kk, gc = col0 + cc;
+        rb[i] = (gk < K && gc < J) ? __ldg(b + (int64_t)gk * J + gc) : 0.0;
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < AV; i++) {
+        const int e = (tid + i * T) * 2, r = e / BK, kk = e % BK;
+        *reinterpret_cast<double2*>(&As[buf][r * LDA + kk]) = make_double2(ra[2 * i], ra[2 * i + 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < BV; i++) {
+        const int e = (tid + i * T) * 2, kk = e / BN, cc = e % BN;
+        *reinterpret_cast<double2*>(&Bs[buf][kk * LDB + cc]) = make_double2(rb[2 * i], rb[2 * i + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < AV; i++) {
+        const int e = tid + i * T, r = e / BK, kk = e % BK;
+        As[buf][r * LDA + kk] = ra[i];
+      }
+#pragma unroll
+      for (int i = 0; i < BV; i++) {
+        const int e = tid + i * T, kk = e / BN, cc = e % BN;
+        Bs[buf][kk * LDB + cc] = rb[i];
+      }
+    }
+  };
+
+  double acc[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; kt++) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+    const double* as = &As[buf][(wr * TM * 8 + g) * LDA + t];
+    const double* bs = &Bs[buf][t * LDB + wc * TN * 8 + g];
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double af[TM], bfr[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) af[i] = as[i * 8 * LDA + ks * 4];
+#pragma unroll
+      for (int j = 0; j < TN; j++) bfr[j] = bs[ks * 4 * LDB + j * 8];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bfr[j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: thread holds C[row g of tile i][cols 2t,2t+1 of tile j]
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    const int gr = row0 + (wr * TM + i) * 8 + g;
+    if (gr >= I) continue;
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+      const int gc = col0 + (wc * TN + j) * 8 + 2 * t;
+      double* p = c + (int64_t)gr * J + gc;
+      if (VEC) {
+        if (gc < J) *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+      } else {
+        if (gc < J) p[0] = acc[i][j][0];
+        if (gc + 1 < J) p[1] = acc[i][j][1];
+      }
+    }
+  }
+}
+
+template <int WR, int WC, int TM, int TN>
+static cudaError_t launch_tiled(cudaStream_t s, const double* A, const double* B, double* C,
+                                int64_t batch, int I, int K, int J, const BatchMap& map, bool vec) {
+  using Cfg = TileCfg<WR, WC, TM, TN>;
+  const int tiles_m = (I + Cfg::BM - 1) / Cfg::BM, tiles_n = (J + Cfg::BN - 1) / Cfg::BN;
+  const int64_t grid = batch * tiles_m * tiles_n;
+  if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  if (vec)
+    gemm_tiled_kernel<WR, WC, TM, TN, true><<<(unsigned)grid, Cfg::THREADS, 0, s>>>(A, B, C, batch, I, K, J, map, tiles_m, tiles_n);
+  else
+    gemm_tiled_kernel<WR, WC, TM, TN, false><<<(unsigned)grid, Cfg::THREADS, 0, s>>>(A, B, C, batch, I, K, J, map, tiles_m, tiles_n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, double* C,
+                          int64_t batch, int I, int K, int J, const BatchMap& map, int sm_count) {
+  if (batch <= 0) return cudaSuccess;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+                         reinterpret_cast<uintptr_t>(C)) & 15) == 0;
+  bool str_even = (map.a_lin < 0 || map.a_lin % 2 == 0) && (map.b_lin < 0 || map.b_lin % 2 == 0);
+  for (int d = 0; d < map.nd; d++) str_even = str_even && (map.a_str[d] % 2 == 0) && (map.b_str[d] % 2 == 0);
+  if (I == 32 && K == 32 && J == 32 && aligned && str_even) {
+    const int64_t grid = (batch + kMM32Warps - 1) / kMM32Warps;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    matmul32_kernel<<<(unsigned)grid, kMM32Warps * 32, 0, s>>>(A, B, C, batch, map);
+    return cudaGetLastError();
+  }
+  const bool vec = aligned && str_even && (K % 2 == 0) && (J % 2 == 0) && (((int64_t)I * J) % 2 == 0);
+  // Tile choice: 64x64 tiles when they still give >= 2 CTAs per SM, else 64x32 (4 warps of 16x32) to
+  // spread a single mid-sized product (e.g. 512^3 -> 128 CTAs) over the 148 SMs, else 16x16 per warp.
+  const int64_t t6464 = batch * ((I + 63) / 64) * ((J + 63) / 64);
+  const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
+  if (I >= 48 && J >= 48 && t6464 >= 2LL * sm_count) return launch_tiled<2, 2, 4, 4>(s, A, B, C, batch, I, K, J, map, vec);
+  if (I >= 48 && J >= 24 && t6432 >= sm_count / 2) return launch_tiled<4, 1, 2, 4>(s, A, B, C, batch, I, K, J, map, vec);
+  if (I > 16 || J > 16) return launch_tiled<2, 1, 2, 4>(s, A, B, C, batch, I, K, J, map, vec);
+  return launch_tiled<1, 1, 2, 2>(s, A, B, C, batch, I, K, J, map, vec);
+}
+
+}  // namespace nd4b

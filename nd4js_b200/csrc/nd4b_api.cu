@@ -1,0 +1,681 @@
+// nd4b_api.cu — the C ABI of include/nd4b.h: context (devices, streams, buffers), the host-buffer
+// entry points (shard over devices -> chunk -> H2D / kernel / D2H pipelined on per-device streams)
+// and the device-resident entry points.  No CPU compute path exists in this library.
+#include "../../include/nd4b.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+using nd4b::BatchMap;
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+const char* ref_message(int code) {
+  switch (code) {
+    case ND4B_E_A_NDIM: return "A must be at least 2D.";
+    case ND4B_E_B_NDIM: return "B must be at least 2D.";
+    case ND4B_E_INNER: return "The last dimension of A and the 2nd to last dimension of B do not match.";
+    case ND4B_E_BROADCAST: return "Shapes are not broadcast-compatible.";
+    case ND4B_E_NOT_SQUARE: return "Last two dimensions must be quadratic.";
+    case ND4B_E_NAN_INPUT: return "Assertion failed.";
+    case ND4B_E_SINGULAR: return "Matrix contains NaNs or is (near) singular.";
+    default: return "nd4b error";
+  }
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(ND4B_E_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, \
+                  __LINE__, cudaGetErrorString(e__));                                         \
+  } while (0)
+
+constexpr int kSlots = 3;     // pipeline depth per device: chunk c runs on slot c % kSlots
+constexpr int kMaxBuf = 6;    // device buffers per slot: up to 2 inputs, 3 outputs, 1 workspace
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  void* buf[kMaxBuf] = {nullptr};
+  size_t cap[kMaxBuf] = {0};
+};
+
+struct Device {
+  int id = -1;
+  int sm_count = 0;
+  Slot slots[kSlots];
+  void* resident[2] = {nullptr, nullptr};  // whole broadcast operands of matmul
+  size_t resident_cap[2] = {0, 0};
+  long long* d_info = nullptr;              // cholesky failure key
+  int* d_ints = nullptr;                    // [0] = svd sweeps, [1] = svd fail flag
+};
+
+struct Context {
+  std::vector<Device> devs;
+  size_t chunk_bytes = 32u << 20;
+  std::mutex mu;
+  std::atomic<uint64_t> calls{0}, launches{0}, h2d{0}, d2h{0}, staged{0};
+  int last_sweeps = 0;
+};
+
+Context* g_ctx = nullptr;
+std::mutex g_init_mu;
+
+int ensure(Slot& s, int i, size_t bytes) {
+  if (s.cap[i] >= bytes) return 0;
+  if (s.buf[i]) CU(cudaFree(s.buf[i]));
+  s.buf[i] = nullptr;
+  s.cap[i] = 0;
+  const size_t want = bytes + bytes / 8 + 256;
+  CU(cudaMalloc(&s.buf[i], want));
+  s.cap[i] = want;
+  return 0;
+}
+
+int ensure_resident(Device& d, int i, size_t bytes) {
+  if (d.resident_cap[i] >= bytes) return 0;
+  if (d.resident[i]) CU(cudaFree(d.resident[i]));
+  d.resident[i] = nullptr;
+  d.resident_cap[i] = 0;
+  CU(cudaMalloc(&d.resident[i], bytes + 256));
+  d.resident_cap[i] = bytes + 256;
+  return 0;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int init_locked(const int* devices, int n) {
+  std::vector<int> ids;
+  if (devices && n > 0) ids.assign(devices, devices + n);
+  else if (const char* env = getenv("ND4B_DEVICES")) {
+    for (const char* p = env; *p;) {
+      char* end;
+      long v = strtol(p, &end, 10);
+      if (end == p) break;
+      ids.push_back((int)v);
+      p = (*end == ',') ? end + 1 : end;
+    }
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(ND4B_E_CUDA, "nd4b: no usable CUDA device (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (ids.empty()) {
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    ids.push_back(cur);
+  }
+  if (g_ctx) {
+    bool same = g_ctx->devs.size() == ids.size();
+    for (size_t i = 0; same && i < ids.size(); i++) same = g_ctx->devs[i].id == ids[i];
+    if (same) return ND4B_OK;
+    return fail(ND4B_E_ARG, "nd4b_init: context already exists with a different device list; call nd4b_shutdown first");
+  }
+  Context* c = new Context();
+  if (const char* mb = getenv("ND4B_CHUNK_MB")) {
+    long v = atol(mb);
+    if (v > 0) c->chunk_bytes = (size_t)v << 20;
+  }
+  for (int id : ids) {
+    if (id < 0 || id >= count) { delete c; return fail(ND4B_E_ARG, "nd4b_init: device %d out of range (count %d)", id, count); }
+    Device d;
+    d.id = id;
+    CU(cudaSetDevice(id));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, id));
+    if (prop.major != 10) { delete c; return fail(ND4B_E_CUDA, "nd4b: device %d is sm_%d%d; this build targets sm_100a (B200) only", id, prop.major, prop.minor); }
+    d.sm_count = prop.multiProcessorCount;
+    for (auto& s : d.slots) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&d.d_info, sizeof(long long)));
+    CU(cudaMalloc(&d.d_ints, 4 * sizeof(int)));
+    c->devs.push_back(d);
+  }
+  g_ctx = c;
+  return ND4B_OK;
+}
+
+int get_ctx(Context** out) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (!g_ctx) {
+    int rc = init_locked(nullptr, 0);
+    if (rc) return rc;
+  }
+  *out = g_ctx;
+  return ND4B_OK;
+}
+
+// ---- generic sharded + chunked pipeline --------------------------------------------------------
+
+struct Stream1 {           // one streamed array: `elems` doubles per unit
+  const double* in = nullptr;
+  double* out = nullptr;
+  int64_t elems = 0;
+};
+
+struct ChunkArgs {
+  Device* dev;
+  cudaStream_t stream;
+  const double* in[2];
+  double* out[3];
+  double* work;
+  size_t work_bytes;
+  int64_t count;   // units in this chunk
+  int64_t base;    // global index of the first unit
+};
+
+// Runs `launch` over `units` independent units: contiguous shards per device, chunks per shard,
+// chunk c of a device on slot c % kSlots (H2D -> kernel -> D2H on one stream; slots overlap).
+int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, const std::vector<Stream1>& outs,
+                 size_t work_bytes_per_unit, const std::function<int(const ChunkArgs&)>& launch) {
+  const int nd = (int)ctx->devs.size();
+  size_t in_bytes_unit = 0, out_bytes_unit = 0;
+  for (auto& s : ins) in_bytes_unit += (size_t)s.elems * 8;
+  for (auto& s : outs) out_bytes_unit += (size_t)s.elems * 8;
+  const size_t per_unit = std::max<size_t>(std::max(in_bytes_unit, out_bytes_unit), 8);
+  const int64_t chunk_units = std::max<int64_t>(1, (int64_t)(ctx->chunk_bytes / per_unit));
+  std::vector<bool> in_pinned, out_pinned;
+  for (auto& s : ins) in_pinned.push_back(is_pinned(s.in));
+  for (auto& s : outs) out_pinned.push_back(is_pinned(s.out));
+
+  struct Shard { int64_t b0, b1, next; int chunk; };
+  std::vector<Shard> shards(nd);
+  for (int d = 0; d < nd; d++) {
+    shards[d].b0 = units * d / nd;
+    shards[d].b1 = units * (d + 1) / nd;
+    shards[d].next = shards[d].b0;
+    shards[d].chunk = 0;
+  }
+  bool progress = true;
+  while (progress) {
+    progress = false;
+    for (int d = 0; d < nd; d++) {
+      Shard& sh = shards[d];
+      if (sh.next >= sh.b1) continue;
+      progress = true;
+      Device& dev = ctx->devs[d];
+      CU(cudaSetDevice(dev.id));
+      Slot& slot = dev.slots[sh.chunk % kSlots];
+      const int64_t cnt = std::min(chunk_units, sh.b1 - sh.next);
+      // the slot's buffers are reused: stream order guarantees the previous chunk on this slot is done
+      ChunkArgs a{};
+      a.dev = &dev;
+      a.stream = slot.stream;
+      a.count = cnt;
+      a.base = sh.next;
+      for (size_t i = 0; i < ins.size(); i++) {
+        const size_t bytes = (size_t)cnt * ins[i].elems * 8;
+        if (int rc = ensure(slot, (int)i, bytes)) return rc;
+        CU(cudaMemcpyAsync(slot.buf[i], ins[i].in + sh.next * ins[i].elems, bytes, cudaMemcpyHostToDevice, slot.stream));
+        ctx->h2d += bytes;
+        if (!in_pinned[i]) ctx->staged += bytes;
+        a.in[i] = static_cast<const double*>(slot.buf[i]);
+      }
+      for (size_t i = 0; i < outs.size(); i++) {
+        const size_t bytes = (size_t)cnt * outs[i].elems * 8;
+        if (int rc = ensure(slot, 2 + (int)i, bytes)) return rc;
+        a.out[i] = static_cast<double*>(slot.buf[2 + i]);
+      }
+      a.work = nullptr;
+      a.work_bytes = 0;
+      if (work_bytes_per_unit) {
+        a.work_bytes = work_bytes_per_unit * (size_t)cnt;
+        if (int rc = ensure(slot, 5, a.work_bytes)) return rc;
+        a.work = static_cast<double*>(slot.buf[5]);
+      }
+      if (int rc = launch(a)) return rc;
+      for (size_t i = 0; i < outs.size(); i++) {
+        const size_t bytes = (size_t)cnt * outs[i].elems * 8;
+        CU(cudaMemcpyAsync(outs[i].out + sh.next * outs[i].elems, a.out[i], bytes, cudaMemcpyDeviceToHost, slot.stream));
+        ctx->d2h += bytes;
+        if (!out_pinned[i]) ctx->staged += bytes;
+      }
+      sh.next += cnt;
+      sh.chunk++;
+    }
+  }
+  for (int d = 0; d < nd; d++) {
+    CU(cudaSetDevice(ctx->devs[d].id));
+    for (auto& s : ctx->devs[d].slots) CU(cudaStreamSynchronize(s.stream));
+  }
+  return ND4B_OK;
+}
+
+int check_cuda_launch(cudaError_t e, Context* ctx, int n = 1) {
+  if (e != cudaSuccess) return fail(ND4B_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  if (ctx) ctx->launches += n;
+  return ND4B_OK;
+}
+
+// Collapses C's leading dims into the BatchMap odometer (strides in elements, 0 = broadcast).
+int build_batch_map(const int32_t* a_shape, int a_ndim, const int32_t* b_shape, int b_ndim,
+                    const int32_t* c_shape, int c_ndim, BatchMap* map, bool* a_full, bool* b_full, int64_t* a_count,
+                    int64_t* b_count) {
+  const int nb = c_ndim - 2;
+  const int64_t I = a_shape[a_ndim - 2], K = a_shape[a_ndim - 1], J = b_shape[b_ndim - 1];
+  std::vector<int64_t> size(nb), as(nb), bs(nb);
+  int64_t sa = I * K, sb = K * J;
+  *a_full = true;
+  *b_full = true;
+  for (int d = nb - 1; d >= 0; d--) {
+    const int da = d - c_ndim + a_ndim, db = d - c_ndim + b_ndim;
+    const int64_t na = da >= 0 ? a_shape[da] : 1, nbb = db >= 0 ? b_shape[db] : 1;
+    size[d] = c_shape[d];
+    as[d] = na > 1 ? sa : 0;
+    bs[d] = nbb > 1 ? sb : 0;
+    if (na != c_shape[d]) *a_full = false;
+    if (nbb != c_shape[d]) *b_full = false;
+    sa *= na;
+    sb *= nbb;
+  }
+  *a_count = sa / (I * K);
+  *b_count = sb / (K * J);
+  // merge adjacent dims when both operands stay affine: stride[d] == size[d+1]*stride[d+1]; drop size-1 dims
+  std::vector<int64_t> ms, mas, mbs;
+  for (int d = 0; d < nb; d++) {
+    if (size[d] == 1) continue;
+    if (!ms.empty() && mas.back() == size[d] * as[d] && mbs.back() == size[d] * bs[d]) {
+      ms.back() *= size[d];
+      mas.back() = as[d];
+      mbs.back() = bs[d];
+    } else {
+      ms.push_back(size[d]);
+      mas.push_back(as[d]);
+      mbs.push_back(bs[d]);
+    }
+  }
+  if (ms.size() > 8) return fail(ND4B_E_ARG, "matmul: more than 8 non-mergeable broadcast dims are not supported");
+  memset(map, 0, sizeof *map);
+  map->nd = (int)ms.size();
+  for (int d = 0; d < map->nd; d++) { map->size[d] = ms[d]; map->a_str[d] = mas[d]; map->b_str[d] = mbs[d]; }
+  return ND4B_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* nd4b_last_error(void) { return g_err.c_str(); }
+const char* nd4b_version(void) { return "nd4b 0.1 (sm_100a)"; }
+
+int nd4b_init(const int* devices, int n_devices) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  return init_locked(devices, n_devices);
+}
+
+int nd4b_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (!g_ctx) return ND4B_OK;
+  for (auto& d : g_ctx->devs) {
+    cudaSetDevice(d.id);
+    for (auto& s : d.slots) {
+      if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+      for (auto& b : s.buf) if (b) cudaFree(b);
+    }
+    for (auto& r : d.resident) if (r) cudaFree(r);
+    if (d.d_info) cudaFree(d.d_info);
+    if (d.d_ints) cudaFree(d.d_ints);
+  }
+  delete g_ctx;
+  g_ctx = nullptr;
+  return ND4B_OK;
+}
+
+int nd4b_device_count(void) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  return g_ctx ? (int)g_ctx->devs.size() : 0;
+}
+
+void* nd4b_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    g_err = std::string("nd4b_host_alloc: ") + cudaGetErrorString(cudaGetLastError());
+    return nullptr;
+  }
+  return p;
+}
+void nd4b_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int nd4b_set_chunk_bytes(size_t bytes) {
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  if (bytes < (1u << 16)) return fail(ND4B_E_ARG, "nd4b_set_chunk_bytes: chunk must be at least 64 KiB");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->chunk_bytes = bytes;
+  return ND4B_OK;
+}
+
+int nd4b_get_stats(nd4b_stats* out) {
+  if (!out) return fail(ND4B_E_ARG, "nd4b_get_stats: null pointer");
+  memset(out, 0, sizeof *out);
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (!g_ctx) return ND4B_OK;
+  out->calls = g_ctx->calls;
+  out->kernel_launches = g_ctx->launches;
+  out->h2d_bytes = g_ctx->h2d;
+  out->d2h_bytes = g_ctx->d2h;
+  out->staged_bytes = g_ctx->staged;
+  out->last_sweeps = g_ctx->last_sweeps;
+  out->n_devices = (int)g_ctx->devs.size();
+  return ND4B_OK;
+}
+
+int nd4b_reset_stats(void) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (!g_ctx) return ND4B_OK;
+  g_ctx->calls = g_ctx->launches = g_ctx->h2d = g_ctx->d2h = g_ctx->staged = 0;
+  return ND4B_OK;
+}
+
+// ---- matmul -------------------------------------------------------------------------------------
+
+int nd4b_matmul_shape(const int32_t* a_shape, int a_ndim, const int32_t* b_shape, int b_ndim,
+                      int32_t* c_shape, int* c_ndim) {
+  if (!a_shape || !b_shape || !c_shape || !c_ndim) return fail(ND4B_E_ARG, "matmul_shape: null pointer");
+  if (a_ndim < 2) return fail(ND4B_E_A_NDIM, "%s", ref_message(ND4B_E_A_NDIM));
+  if (b_ndim < 2) return fail(ND4B_E_B_NDIM, "%s", ref_message(ND4B_E_B_NDIM));
+  if (a_ndim > ND4B_MAX_NDIM || b_ndim > ND4B_MAX_NDIM) return fail(ND4B_E_ARG, "matmul: ndim > %d", ND4B_MAX_NDIM);
+  for (int d = 0; d < a_ndim; d++) if (a_shape[d] < 1) return fail(ND4B_E_ARG, "Invalid shape: dims must be >= 1.");
+  for (int d = 0; d < b_ndim; d++) if (b_shape[d] < 1) return fail(ND4B_E_ARG, "Invalid shape: dims must be >= 1.");
+  const int32_t I = a_shape[a_ndim - 2], K = a_shape[a_ndim - 1], J = b_shape[b_ndim - 1];
+  if (b_shape[b_ndim - 2] != K) return fail(ND4B_E_INNER, "%s", ref_message(ND4B_E_INNER));
+  const int ndim = std::max(a_ndim, b_ndim);
+  for (int d = 0; d < ndim; d++) c_shape[d] = 1;
+  c_shape[ndim - 2] = I;
+  c_shape[ndim - 1] = J;
+  const int32_t* shp[2] = {a_shape, b_shape};
+  const int nds[2] = {a_ndim, b_ndim};
+  for (int w = 0; w < 2; w++)
+    for (int i = ndim - 2, j = nds[w] - 2; i-- > 0 && j-- > 0;) {
+      if (c_shape[i] == 1) c_shape[i] = shp[w][j];
+      else if (c_shape[i] != shp[w][j] && shp[w][j] != 1) return fail(ND4B_E_BROADCAST, "%s", ref_message(ND4B_E_BROADCAST));
+    }
+  *c_ndim = ndim;
+  return ND4B_OK;
+}
+
+int nd4b_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
+                    const double* B, const int32_t* b_shape, int b_ndim,
+                    double* C, const int32_t* c_shape, int c_ndim) {
+  if (!A || !B || !C || !c_shape) return fail(ND4B_E_ARG, "matmul: null pointer");
+  int32_t want[ND4B_MAX_NDIM];
+  int want_nd = 0;
+  if (int rc = nd4b_matmul_shape(a_shape, a_ndim, b_shape, b_ndim, want, &want_nd)) return rc;
+  if (want_nd != c_ndim) return fail(ND4B_E_SHAPE, "matmul: result ndim %d, expected %d", c_ndim, want_nd);
+  for (int d = 0; d < c_ndim; d++)
+    if (want[d] != c_shape[d]) return fail(ND4B_E_SHAPE, "matmul: result shape mismatch at dim %d", d);
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+
+  const int I = a_shape[a_ndim - 2], K = a_shape[a_ndim - 1], J = b_shape[b_ndim - 1];
+  BatchMap map;
+  bool a_full, b_full;
+  int64_t a_count, b_count;
+  if (int rc = build_batch_map(a_shape, a_ndim, b_shape, b_ndim, c_shape, c_ndim, &map, &a_full, &b_full, &a_count, &b_count)) return rc;
+  int64_t batch = 1;
+  for (int d = 0; d < c_ndim - 2; d++) batch *= c_shape[d];
+  const int64_t a_elems = (int64_t)I * K, b_elems = (int64_t)K * J, c_elems = (int64_t)I * J;
+  const int nd = (int)ctx->devs.size();
+
+  // Row-panel split of a single large product over the devices (B replicated, A and C split by rows).
+  if (batch == 1 && nd > 1 && I >= 256 * nd) {
+    for (int d = 0; d < nd; d++) {
+      Device& dev = ctx->devs[d];
+      CU(cudaSetDevice(dev.id));
+      Slot& slot = dev.slots[0];
+      const int r0 = (int)((int64_t)I * d / nd), r1 = (int)((int64_t)I * (d + 1) / nd);
+      const size_t ab = (size_t)(r1 - r0) * K * 8, bb = (size_t)b_elems * 8, cb = (size_t)(r1 - r0) * J * 8;
+      if (int rc = ensure(slot, 0, ab)) return rc;
+      if (int rc = ensure(slot, 1, bb)) return rc;
+      if (int rc = ensure(slot, 2, cb)) return rc;
+      CU(cudaMemcpyAsync(slot.buf[0], A + (int64_t)r0 * K, ab, cudaMemcpyHostToDevice, slot.stream));
+      CU(cudaMemcpyAsync(slot.buf[1], B, bb, cudaMemcpyHostToDevice, slot.stream));
+      BatchMap m1;
+      memset(&m1, 0, sizeof m1);
+      if (int rc = check_cuda_launch(nd4b::launch_matmul(slot.stream, (const double*)slot.buf[0], (const double*)slot.buf[1],
+                                                         (double*)slot.buf[2], 1, r1 - r0, K, J, m1, dev.sm_count), ctx)) return rc;
+      CU(cudaMemcpyAsync(C + (int64_t)r0 * J, slot.buf[2], cb, cudaMemcpyDeviceToHost, slot.stream));
+      ctx->h2d += ab + bb;
+      ctx->d2h += cb;
+    }
+    for (int d = 0; d < nd; d++) {
+      CU(cudaSetDevice(ctx->devs[d].id));
+      CU(cudaStreamSynchronize(ctx->devs[d].slots[0].stream));
+    }
+    return ND4B_OK;
+  }
+
+  // Operands that follow C's batch index one-to-one are streamed in chunks; operands with any broadcast
+  // dim are made resident on every device once and addressed through the odometer.
+  std::vector<Stream1> ins, outs;
+  int a_slot = -1, b_slot = -1;
+  if (a_full) { a_slot = (int)ins.size(); ins.push_back({A, nullptr, a_elems}); }
+  if (b_full) { b_slot = (int)ins.size(); ins.push_back({B, nullptr, b_elems}); }
+  outs.push_back({nullptr, C, c_elems});
+  for (int d = 0; d < nd; d++) {
+    Device& dev = ctx->devs[d];
+    CU(cudaSetDevice(dev.id));
+    if (!a_full) {
+      const size_t bytes = (size_t)a_count * a_elems * 8;
+      if (int rc = ensure_resident(dev, 0, bytes)) return rc;
+      CU(cudaMemcpyAsync(dev.resident[0], A, bytes, cudaMemcpyHostToDevice, dev.slots[0].stream));
+      ctx->h2d += bytes;
+    }
+    if (!b_full) {
+      const size_t bytes = (size_t)b_count * b_elems * 8;
+      if (int rc = ensure_resident(dev, 1, bytes)) return rc;
+      CU(cudaMemcpyAsync(dev.resident[1], B, bytes, cudaMemcpyHostToDevice, dev.slots[0].stream));
+      ctx->h2d += bytes;
+    }
+    if (!a_full || !b_full) CU(cudaStreamSynchronize(dev.slots[0].stream));
+  }
+  auto launch = [&](const ChunkArgs& a) -> int {
+    BatchMap m = map;
+    m.base = a.base;
+    m.a_lin = a_full ? a_elems : (a_count == 1 ? 0 : -1);
+    m.b_lin = b_full ? b_elems : (b_count == 1 ? 0 : -1);
+    const double* ap = a_full ? a.in[a_slot] : static_cast<const double*>(a.dev->resident[0]);
+    const double* bp = b_full ? a.in[b_slot] : static_cast<const double*>(a.dev->resident[1]);
+    return check_cuda_launch(nd4b::launch_matmul(a.stream, ap, bp, a.out[0], a.count, I, K, J, m, a.dev->sm_count), ctx);
+  };
+  return run_pipeline(ctx, batch, ins, outs, 0, launch);
+}
+
+// ---- cholesky -----------------------------------------------------------------------------------
+
+int nd4b_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t* first_bad) {
+  if (first_bad) *first_bad = -1;
+  if (!S || !L) return fail(ND4B_E_ARG, "cholesky: null pointer");
+  if (batch < 1 || n < 1) return fail(ND4B_E_ARG, "cholesky: batch and n must be >= 1");
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  const long long none = LLONG_MAX;
+  for (auto& d : ctx->devs) {
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpy(d.d_info, &none, sizeof none, cudaMemcpyHostToDevice));
+  }
+  const int64_t nn = (int64_t)n * n;
+  auto launch = [&](const ChunkArgs& a) -> int {
+    return check_cuda_launch(nd4b::launch_cholesky(a.stream, a.in[0], a.out[0], a.count, n, a.dev->d_info, a.base), ctx);
+  };
+  if (int rc = run_pipeline(ctx, batch, {{S, nullptr, nn}}, {{nullptr, L, nn}}, 0, launch)) return rc;
+  long long key = LLONG_MAX;
+  for (auto& d : ctx->devs) {
+    long long k;
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpy(&k, d.d_info, sizeof k, cudaMemcpyDeviceToHost));
+    key = std::min(key, k);
+  }
+  if (key != LLONG_MAX) {
+    if (first_bad) *first_bad = key >> 1;
+    const int code = (key & 1) ? ND4B_E_SINGULAR : ND4B_E_NAN_INPUT;
+    return fail(code, "%s", ref_message(code));
+  }
+  return ND4B_OK;
+}
+
+// ---- qr -----------------------------------------------------------------------------------------
+
+int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
+  if (!A || !Q || !R) return fail(ND4B_E_ARG, "qr: null pointer");
+  if (batch < 1 || rows < 1 || cols < 1) return fail(ND4B_E_ARG, "qr: batch, rows and cols must be >= 1");
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  const int L = std::min(rows, cols);
+  const size_t work_unit = nd4b::qr_workspace_bytes(1, rows, cols);
+  auto launch = [&](const ChunkArgs& a) -> int {
+    return check_cuda_launch(nd4b::launch_qr(a.stream, a.in[0], a.out[0], a.out[1], a.count, rows, cols, a.work, a.work_bytes), ctx);
+  };
+  return run_pipeline(ctx, batch, {{A, nullptr, (int64_t)rows * cols}},
+                      {{nullptr, Q, (int64_t)rows * L}, {nullptr, R, (int64_t)L * cols}}, work_unit, launch);
+}
+
+// ---- svd ----------------------------------------------------------------------------------------
+
+int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
+                      int64_t batch, int rows, int cols, int* sweeps_out) {
+  if (sweeps_out) *sweeps_out = 0;
+  if (!A || !U || !sv || !V) return fail(ND4B_E_ARG, "svd_jac_1sided: null pointer");
+  if (batch < 1 || rows < 1 || cols < 1) return fail(ND4B_E_ARG, "svd_jac_1sided: batch, rows and cols must be >= 1");
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  for (auto& d : ctx->devs) {
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemset(d.d_ints, 0, 4 * sizeof(int)));
+  }
+  const int L = std::min(rows, cols);
+  const size_t work_unit = nd4b::svd_workspace_bytes(1, rows, cols);
+  auto launch = [&](const ChunkArgs& a) -> int {
+    return check_cuda_launch(nd4b::launch_svd_jac1(a.stream, a.in[0], a.out[0], a.out[1], a.out[2], a.count, rows, cols,
+                                                   a.dev->d_ints, a.dev->d_ints + 1, a.work, a.work_bytes), ctx);
+  };
+  if (int rc = run_pipeline(ctx, batch, {{A, nullptr, (int64_t)rows * cols}},
+                            {{nullptr, U, (int64_t)rows * L}, {nullptr, sv, (int64_t)L}, {nullptr, V, (int64_t)L * cols}},
+                            work_unit, launch)) return rc;
+  int sweeps = 0, failed = 0;
+  for (auto& d : ctx->devs) {
+    int h[2];
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpy(h, d.d_ints, sizeof h, cudaMemcpyDeviceToHost));
+    sweeps = std::max(sweeps, h[0]);
+    failed |= h[1];
+  }
+  ctx->last_sweeps = sweeps;
+  if (sweeps_out) *sweeps_out = sweeps;
+  if (failed) return fail(ND4B_E_NO_CONVERGENCE, "svd_jac_1sided: no convergence within the sweep limit (NaN or Inf in A?)");
+  return ND4B_OK;
+}
+
+// ---- device-resident forms ----------------------------------------------------------------------
+
+static int dev_enter(int device, Context** ctx, int* sm_count) {
+  if (int rc = get_ctx(ctx)) return rc;
+  CU(cudaSetDevice(device));
+  *sm_count = 148;
+  for (auto& d : (*ctx)->devs) if (d.id == device) *sm_count = d.sm_count;
+  return ND4B_OK;
+}
+
+int nd4b_dev_matmul_f64(int device, void* stream, const double* A, int64_t a_stride,
+                        const double* B, int64_t b_stride, double* C, int64_t batch, int I, int K, int J) {
+  if (!A || !B || !C || batch < 1 || I < 1 || K < 1 || J < 1 || a_stride < 0 || b_stride < 0)
+    return fail(ND4B_E_ARG, "dev_matmul: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  BatchMap m;
+  memset(&m, 0, sizeof m);
+  m.a_lin = a_stride;
+  m.b_lin = b_stride;
+  return check_cuda_launch(nd4b::launch_matmul((cudaStream_t)stream, A, B, C, batch, I, K, J, m, sms), ctx);
+}
+
+int nd4b_dev_cholesky_f64(int device, void* stream, const double* S, double* L, int64_t batch, int n, long long* info) {
+  if (!S || !L || batch < 1 || n < 1) return fail(ND4B_E_ARG, "dev_cholesky: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  return check_cuda_launch(nd4b::launch_cholesky((cudaStream_t)stream, S, L, batch, n, info, 0), ctx);
+}
+
+size_t nd4b_dev_qr_workspace(int64_t batch, int rows, int cols) { return nd4b::qr_workspace_bytes(batch, rows, cols); }
+size_t nd4b_dev_svd_workspace(int64_t batch, int rows, int cols) { return nd4b::svd_workspace_bytes(batch, rows, cols); }
+
+int nd4b_dev_qr_f64(int device, void* stream, const double* A, double* Q, double* R,
+                    int64_t batch, int rows, int cols, double* workspace, size_t workspace_bytes) {
+  if (!A || !Q || !R || batch < 1 || rows < 1 || cols < 1) return fail(ND4B_E_ARG, "dev_qr: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  return check_cuda_launch(nd4b::launch_qr((cudaStream_t)stream, A, Q, R, batch, rows, cols, workspace, workspace_bytes), ctx);
+}
+
+int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, double* sv, double* V,
+                          int64_t batch, int rows, int cols, int* sweeps, double* workspace, size_t workspace_bytes) {
+  if (!A || !U || !sv || !V || batch < 1 || rows < 1 || cols < 1) return fail(ND4B_E_ARG, "dev_svd: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  return check_cuda_launch(nd4b::launch_svd_jac1((cudaStream_t)stream, A, U, sv, V, batch, rows, cols, sweeps, nullptr,
+                                                 workspace, workspace_bytes), ctx);
+}
+
+// FP64 pipe probes (not part of the nd.la surface; used by tools/fp64_peak.py and bench.py).
+int nd4b_probe_fp64(int device, int which, int iters, int blocks, int threads, float* ms_out) {
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  double* out;
+  CU(cudaMalloc(&out, 64));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  auto run = [&]() { return which == 0 ? nd4b::launch_probe_dfma(0, out, iters, blocks, threads) : nd4b::launch_probe_dmma(0, out, iters, blocks, threads); };
+  CU(run());
+  CU(cudaDeviceSynchronize());
+  CU(cudaEventRecord(e0, 0));
+  CU(run());
+  CU(cudaEventRecord(e1, 0));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return ND4B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+/* nd4ref.h — CPU ORACLE for the nd4js batched dense-LA hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (libnd4b.so) never links or calls anything in oracle/.
+ *
+ * Each function is a plain-C restatement (single thread, IEEE-754 binary64, no FMA
+ * contraction: build with -ffp-contract=off) of one nd4js v1.3.0 routine; the cited
+ * file:line ranges are relative to the reference checkout.
+ *
+ * Pinning status: the reference ships NO stored numeric vectors for these
+ * four routines and no JS engine exists in this image, so value-level parity is pinned by
+ * this restatement only.  What the reference's own tests DO pin, and tests/ checks against
+ * this oracle:  matmul known answers (src/la/matmul_test.js:32-78), the cholesky docstring
+ * example (src/help.js:1876-1885), exactness of svd_jac* on diagonal input
+ * (src/la/_generic_test_svd_decomp.js:180-216) and the property suites with the
+ * reference's tolerances (qr_test.js:169-187, cholesky_test.js:72-123,
+ * _generic_test_svd_decomp.js:79-163).  nd.la.svd_jac_1sided does not exist in the
+ * reference snapshot: for it PARITY IS UNPINNED by the reference; the oracle's
+ * svd_jac_2sided restatement supplies the singular values it is compared with.
+ */
+#ifndef ND4REF_H
+#define ND4REF_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes shared with include/nd4b.h */
+#define ND4REF_OK                 0
+#define ND4REF_E_A_NDIM         (-1)  /* 'A must be at least 2D.'                        matmul.js:95  */
+#define ND4REF_E_B_NDIM         (-2)  /* 'B must be at least 2D.'                        matmul.js:96  */
+#define ND4REF_E_INNER          (-3)  /* 'The last dimension of A and the 2nd to last…'  matmul.js:101 */
+#define ND4REF_E_BROADCAST      (-4)  /* 'Shapes are not broadcast-compatible.'          matmul.js:116 */
+#define ND4REF_E_SHAPE          (-5)  /* caller-supplied result shape does not match                   */
+#define ND4REF_E_NOT_SQUARE     (-6)  /* 'Last two dimensions must be quadratic.'        cholesky.js:61 */
+#define ND4REF_E_NAN_INPUT      (-7)  /* KahanSum.set 'Assertion failed.'                kahan_sum.js:29 */
+#define ND4REF_E_SINGULAR         1   /* 'Matrix contains NaNs or is (near) singular.'   cholesky.js:44 */
+
+/* matmul2: shape inference, src/la/matmul.js:91-116.  c_shape must hold max(a_ndim,b_ndim) ints. */
+int nd4ref_matmul_shape(const int32_t* a_shape, int a_ndim,
+                        const int32_t* b_shape, int b_ndim,
+                        int32_t* c_shape, int* c_ndim);
+
+/* matmul2_RR: src/la/matmul.js:31-74 (i-k-j order, separate mul and add, C zeroed first). */
+int nd4ref_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
+                      const double* B, const int32_t* b_shape, int b_ndim,
+                      double* C, const int32_t* c_shape, int c_ndim);
+
+/* cholesky_decomp: src/la/cholesky.js:27-72 + src/kahan_sum.js:19-42.
+ * returns 0, ND4REF_E_SINGULAR (first_bad = batch index of first failing matrix) or <0. */
+int nd4ref_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t* first_bad);
+
+/* qr_decomp: src/la/qr.js:80-145 (rows>cols: Givens, thin) and :27-77 (rows<=cols: qr_decomp_full).
+ * Q is [batch,rows,min(rows,cols)], R is [batch,min(rows,cols),cols]. */
+int nd4ref_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols);
+
+/* svd_jac_2sided: src/la/svd_jac_2sided.js:30-144 + src/la/_svd_jac_utils.js:72-188.
+ * U [batch,rows,L], sv [batch,L], V [batch,L,cols], L=min(rows,cols); A = U diag(sv) V.
+ * sweeps_out (may be NULL) receives the maximum number of sweeps over the batch. */
+int nd4ref_svd_jac2_f64(const double* A, double* U, double* sv, double* V,
+                        int64_t batch, int rows, int cols, int* sweeps_out);
+
+/* scalar helpers exposed for unit tests */
+void nd4ref_giv_rot_qr(double a, double b, double out_c_s_norm[3]);      /* _giv_rot.js:22-37   */
+void nd4ref_svd_jac_angles(double Spp, double Spq, double Sqp, double Sqq,
+                           double out_ca_sa_cb_sb[4]);                   /* _svd_jac_utils.js:72-114 */
+double nd4ref_frobenius(const double* x, int64_t n);                     /* norm.js:22-68       */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
