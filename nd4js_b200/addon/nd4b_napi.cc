@@ -1,0 +1,182 @@
+// nd4b_napi.cc — Node.js N-API addon: a thin, synchronous binding of the C ABI in include/nd4b.h.
+//
+// Every export takes typed arrays owned by the JS caller (Float64Array data, Int32Array shapes), reads
+// the inputs only for the duration of the call, fills caller-allocated outputs and retains nothing —
+// the ownership/threading contract of the reference's nd.la functions.  Errors are
+// thrown as JS Error objects carrying the reference's own message text (nd4b_last_error()).
+// There is no CPU fallback: without a usable B200 every call throws.
+//
+// The image has no Node.js; this file is compile-checked against node_api_min.h (tests/test_addon.py).
+#ifdef ND4B_HAVE_NODE_API
+#include <node_api.h>
+#else
+#include "node_api_min.h"
+#endif
+#include "../../include/nd4b.h"
+
+#include <stdint.h>
+#include <string.h>
+
+namespace {
+
+struct F64 { double* p; size_t n; };
+struct I32 { int32_t* p; size_t n; };
+
+bool get_f64(napi_env env, napi_value v, F64* out) {
+  napi_typedarray_type t; void* data; size_t len;
+  if (napi_get_typedarray_info(env, v, &t, &len, &data, nullptr, nullptr) != napi_ok || t != napi_float64_array) {
+    napi_throw_error(env, nullptr, "nd4b: expected a Float64Array");
+    return false;
+  }
+  out->p = static_cast<double*>(data); out->n = len;
+  return true;
+}
+bool get_i32(napi_env env, napi_value v, I32* out) {
+  napi_typedarray_type t; void* data; size_t len;
+  if (napi_get_typedarray_info(env, v, &t, &len, &data, nullptr, nullptr) != napi_ok || t != napi_int32_array) {
+    napi_throw_error(env, nullptr, "nd4b: expected an Int32Array");
+    return false;
+  }
+  out->p = static_cast<int32_t*>(data); out->n = len;
+  return true;
+}
+bool get_int(napi_env env, napi_value v, int64_t* out) {
+  if (napi_get_value_int64(env, v, out) != napi_ok) { napi_throw_error(env, nullptr, "nd4b: expected an integer"); return false; }
+  return true;
+}
+napi_value undefined(napi_env env) { napi_value u; napi_get_undefined(env, &u); return u; }
+napi_value fail(napi_env env) { napi_throw_error(env, nullptr, nd4b_last_error()); return nullptr; }
+int64_t prod(const I32& s) { int64_t p = 1; for (size_t i = 0; i < s.n; i++) p *= s.p[i]; return p; }
+
+// matmulShape(aShape:Int32Array, bShape:Int32Array, cShape:Int32Array) -> ndim
+napi_value MatmulShape(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value a[3];
+  napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
+  I32 as, bs, cs;
+  if (argc < 3 || !get_i32(env, a[0], &as) || !get_i32(env, a[1], &bs) || !get_i32(env, a[2], &cs)) return nullptr;
+  if (cs.n < (as.n > bs.n ? as.n : bs.n)) { napi_throw_error(env, nullptr, "nd4b: cShape too short"); return nullptr; }
+  int nd = 0;
+  if (nd4b_matmul_shape(as.p, (int)as.n, bs.p, (int)bs.n, cs.p, &nd)) return fail(env);
+  napi_value r; napi_create_int32(env, nd, &r); return r;
+}
+
+// matmul(a:Float64Array, aShape, b:Float64Array, bShape, c:Float64Array, cShape)
+napi_value Matmul(napi_env env, napi_callback_info info) {
+  size_t argc = 6; napi_value v[6];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 a, b, c; I32 as, bs, cs;
+  if (argc < 6 || !get_f64(env, v[0], &a) || !get_i32(env, v[1], &as) || !get_f64(env, v[2], &b) ||
+      !get_i32(env, v[3], &bs) || !get_f64(env, v[4], &c) || !get_i32(env, v[5], &cs)) return nullptr;
+  if ((int64_t)a.n != prod(as) || (int64_t)b.n != prod(bs) || (int64_t)c.n != prod(cs)) {
+    napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
+  }
+  if (nd4b_matmul_f64(a.p, as.p, (int)as.n, b.p, bs.p, (int)bs.n, c.p, cs.p, (int)cs.n)) return fail(env);
+  return undefined(env);
+}
+
+// cholesky(S:Float64Array, L:Float64Array, batch, n)
+napi_value Cholesky(napi_env env, napi_callback_info info) {
+  size_t argc = 4; napi_value v[4];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 s, l; int64_t batch, n;
+  if (argc < 4 || !get_f64(env, v[0], &s) || !get_f64(env, v[1], &l) || !get_int(env, v[2], &batch) || !get_int(env, v[3], &n)) return nullptr;
+  if ((int64_t)s.n != batch * n * n || l.n != s.n) { napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr; }
+  int64_t bad = -1;
+  if (nd4b_cholesky_f64(s.p, l.p, batch, (int)n, &bad)) return fail(env);
+  return undefined(env);
+}
+
+// qr(A, Q, R, batch, rows, cols)
+napi_value Qr(napi_env env, napi_callback_info info) {
+  size_t argc = 6; napi_value v[6];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 a, q, r; int64_t batch, rows, cols;
+  if (argc < 6 || !get_f64(env, v[0], &a) || !get_f64(env, v[1], &q) || !get_f64(env, v[2], &r) ||
+      !get_int(env, v[3], &batch) || !get_int(env, v[4], &rows) || !get_int(env, v[5], &cols)) return nullptr;
+  const int64_t l = rows < cols ? rows : cols;
+  if ((int64_t)a.n != batch * rows * cols || (int64_t)q.n != batch * rows * l || (int64_t)r.n != batch * l * cols) {
+    napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
+  }
+  if (nd4b_qr_f64(a.p, q.p, r.p, batch, (int)rows, (int)cols)) return fail(env);
+  return undefined(env);
+}
+
+// svdJac1(A, U, sv, V, batch, rows, cols) -> sweeps
+napi_value SvdJac1(napi_env env, napi_callback_info info) {
+  size_t argc = 7; napi_value v[7];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 a, u, s, vt; int64_t batch, rows, cols;
+  if (argc < 7 || !get_f64(env, v[0], &a) || !get_f64(env, v[1], &u) || !get_f64(env, v[2], &s) || !get_f64(env, v[3], &vt) ||
+      !get_int(env, v[4], &batch) || !get_int(env, v[5], &rows) || !get_int(env, v[6], &cols)) return nullptr;
+  const int64_t l = rows < cols ? rows : cols;
+  if ((int64_t)a.n != batch * rows * cols || (int64_t)u.n != batch * rows * l || (int64_t)s.n != batch * l ||
+      (int64_t)vt.n != batch * l * cols) {
+    napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
+  }
+  int sweeps = 0;
+  if (nd4b_svd_jac1_f64(a.p, u.p, s.p, vt.p, batch, (int)rows, (int)cols, &sweeps)) return fail(env);
+  napi_value r; napi_create_int32(env, sweeps, &r); return r;
+}
+
+void free_pinned(napi_env, void* data, void*) { nd4b_host_free(data); }
+
+// pinnedFloat64Array(length) -> Float64Array backed by page-locked memory (skips the staging copy)
+napi_value PinnedFloat64Array(napi_env env, napi_callback_info info) {
+  size_t argc = 1; napi_value v[1];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  int64_t n;
+  if (argc < 1 || !get_int(env, v[0], &n) || n < 0) return nullptr;
+  void* p = nd4b_host_alloc((size_t)n * sizeof(double));
+  if (!p) return fail(env);
+  memset(p, 0, (size_t)n * sizeof(double));
+  napi_value ab, ta;
+  if (napi_create_external_arraybuffer(env, p, (size_t)n * sizeof(double), free_pinned, nullptr, &ab) != napi_ok) {
+    nd4b_host_free(p); napi_throw_error(env, nullptr, "nd4b: external ArrayBuffers are not allowed in this runtime"); return nullptr;
+  }
+  napi_create_typedarray(env, napi_float64_array, (size_t)n, ab, 0, &ta);
+  return ta;
+}
+
+// init(devices:Int32Array) ; deviceCount() ; stats()
+napi_value Init(napi_env env, napi_callback_info info) {
+  size_t argc = 1; napi_value v[1];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  I32 d{nullptr, 0};
+  if (argc >= 1 && !get_i32(env, v[0], &d)) return nullptr;
+  if (nd4b_init(d.p, (int)d.n)) return fail(env);
+  return undefined(env);
+}
+napi_value DeviceCount(napi_env env, napi_callback_info) { napi_value r; napi_create_int32(env, nd4b_device_count(), &r); return r; }
+napi_value Stats(napi_env env, napi_callback_info) {
+  nd4b_stats s;
+  if (nd4b_get_stats(&s)) return fail(env);
+  napi_value o, x; napi_create_object(env, &o);
+  napi_create_double(env, (double)s.calls, &x); napi_set_named_property(env, o, "calls", x);
+  napi_create_double(env, (double)s.kernel_launches, &x); napi_set_named_property(env, o, "kernelLaunches", x);
+  napi_create_double(env, (double)s.h2d_bytes, &x); napi_set_named_property(env, o, "h2dBytes", x);
+  napi_create_double(env, (double)s.d2h_bytes, &x); napi_set_named_property(env, o, "d2hBytes", x);
+  napi_create_int32(env, s.last_sweeps, &x); napi_set_named_property(env, o, "lastSweeps", x);
+  napi_create_int32(env, s.n_devices, &x); napi_set_named_property(env, o, "devices", x);
+  return o;
+}
+
+napi_value RegisterAll(napi_env env, napi_value exports) {
+  const napi_property_descriptor props[] = {
+      {"matmulShape", nullptr, MatmulShape, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"matmul", nullptr, Matmul, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"cholesky", nullptr, Cholesky, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"qr", nullptr, Qr, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"svdJac1", nullptr, SvdJac1, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"pinnedFloat64Array", nullptr, PinnedFloat64Array, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"init", nullptr, Init, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"deviceCount", nullptr, DeviceCount, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"stats", nullptr, Stats, nullptr, nullptr, nullptr, napi_default, nullptr},
+  };
+  napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
+  return exports;
+}
+
+napi_module g_module = {1, 0, __FILE__, RegisterAll, "nd4b", nullptr, {nullptr, nullptr, nullptr, nullptr}};
+__attribute__((constructor)) void register_nd4b() { napi_module_register(&g_module); }
+
+}  // namespace

@@ -1,0 +1,107 @@
+'use strict';
+// nd4b JS shim — drop-in replacements for the nd4js functions on the batched dense-LA hot path.
+// Same names, signatures, result shapes and error texts as the reference:
+//   matmul2 / matmul       nd4js src/la/matmul.js:91-147, :150-236
+//   cholesky_decomp        nd4js src/la/cholesky.js:50-72
+//   qr_decomp              nd4js src/la/qr.js:80-145
+//   svd_jac_1sided         contract of nd4js src/la/svd_jac_2sided.js:30-144 (new export)
+// asarray(), dtype upcasts and the matrix-chain ordering stay in JS exactly as in the reference;
+// the arithmetic is done by the N-API addon (addon/nd4b_napi.cc -> libnd4b.so -> CUDA on B200).
+// Float64 only; there is no CPU fallback: other dtypes and a missing GPU throw.
+const nd = require('nd4js');
+const addon = require('../addon/build/Release/nd4b.node');
+const {NDArray, asarray} = nd;
+
+function f64(a, who) {
+  if (a.dtype === 'float64') return a.data;
+  if (a.dtype === 'int32') return Float64Array.from(a.data); // upcast as qr.js:93 / cholesky.js:58 do
+  throw new Error(`${who}: dtype '${a.dtype}' is not supported by the GPU path (float64 only).`);
+}
+
+function matmul2(a, b) {
+  a = asarray(a); b = asarray(b);
+  if (a.ndim < 2) throw new Error('A must be at least 2D.');
+  if (b.ndim < 2) throw new Error('B must be at least 2D.');
+  const shape = new Int32Array(Math.max(a.ndim, b.ndim));
+  addon.matmulShape(a.shape, b.shape, shape); // throws the reference's texts on mismatch
+  const c = new Float64Array(shape.reduce((m, n) => m * n, 1));
+  addon.matmul(f64(a, 'matmul2'), a.shape, f64(b, 'matmul2'), b.shape, c, shape);
+  return new NDArray(shape, c);
+}
+
+function matmul(...matrices) {
+  matrices = matrices.map(m => asarray(m));
+  if (matrices.length === 1) return matrices[0];
+  if (matrices.length === 2) return matmul2(...matrices);
+  // chain ordering by broadcast-aware flop counts, as matmul.js:159-235
+  const nOps = (sa, sb) => {
+    const ndim = Math.max(sa.length, sb.length), shape = new Int32Array(ndim).fill(1);
+    if (sb[sb.length - 2] !== sa[sa.length - 1]) throw new Error('Shape mismatch.');
+    shape[ndim - 2] = sa[sa.length - 2]; shape[ndim - 1] = sb[sb.length - 1];
+    for (const shp of [sa, sb])
+      for (let i = ndim - 2, j = shp.length - 2; i-- > 0 && j-- > 0;)
+        if (shape[i] === 1) shape[i] = shp[j];
+        else if (shape[i] !== shp[j] && shp[j] !== 1) throw new Error('Shapes are not broadcast-compatible.');
+    return [shape.reduce((x, y) => x * y, 1) * sa[sa.length - 1], shape];
+  };
+  const n = matrices.length, op = Array.from({length: n}, () => []);
+  for (let i = 0; i < n; i++) op[i][i] = [0, matrices[i].shape];
+  for (let len = 2; len <= n; len++)
+    for (let i = 0; i <= n - len; i++) {
+      let best = Infinity, bestShape;
+      for (let j = 1; j < len; j++) {
+        const [lf, ls] = op[i][i + j - 1], [rf, rs] = op[i + j][i + len - 1];
+        let [f, s] = nOps(ls, rs); f += lf + rf;
+        if (f < best) { best = f; bestShape = s; }
+      }
+      if (bestShape === undefined) throw new Error('Integer overflow (too many FLOPs).');
+      op[i][i + len - 1] = [best, bestShape];
+    }
+  const product = (from, to) => {
+    if (from === to) return matrices[from];
+    let best = Infinity, idx;
+    for (let i = from; i < to; i++) {
+      const [lf, ls] = op[from][i], [rf, rs] = op[i + 1][to];
+      let [f] = nOps(ls, rs); f += lf + rf;
+      if (f < best) { best = f; idx = i; }
+    }
+    return matmul2(product(from, idx), product(idx + 1, to));
+  };
+  return product(0, n - 1);
+}
+
+function cholesky_decomp(S) {
+  S = asarray(S);
+  const [N, M] = S.shape.slice(-2);
+  if (N !== M) throw new Error('Last two dimensions must be quadratic.');
+  const s = f64(S, 'cholesky_decomp'), L = new Float64Array(s.length);
+  addon.cholesky(s, L, s.length / (N * N), N); // throws 'Matrix contains NaNs or is (near) singular.'
+  return new NDArray(S.shape, L);
+}
+
+function qr_decomp(A) {
+  A = asarray(A);
+  if (A.ndim < 2) throw new Error('qr_decomp(A): A.ndim must be at least 2.');
+  const [N, M] = A.shape.slice(-2), L = Math.min(N, M), a = f64(A, 'qr_decomp'), batch = a.length / (N * M);
+  const qShape = Int32Array.from(A.shape), rShape = Int32Array.from(A.shape);
+  qShape[qShape.length - 1] = L; rShape[rShape.length - 2] = L;
+  const Q = new Float64Array(batch * N * L), R = new Float64Array(batch * L * M);
+  addon.qr(a, Q, R, batch, N, M);
+  return [new NDArray(qShape, Q), new NDArray(rShape, R)];
+}
+
+function svd_jac_1sided(A) {
+  A = asarray(A);
+  if (A.dtype.startsWith('complex')) throw new Error('svd_jac_1sided(A): A.dtype must be float.');
+  if (A.ndim < 2) throw new Error('svd_jac_1sided(A): A.ndim must be at least 2.');
+  const [N, M] = A.shape.slice(-2), L = Math.min(N, M), a = f64(A, 'svd_jac_1sided'), batch = a.length / (N * M);
+  const uShape = Int32Array.from(A.shape), vShape = Int32Array.from(A.shape), sShape = A.shape.slice(0, -1);
+  uShape[uShape.length - 1] = L; vShape[vShape.length - 2] = L; sShape[sShape.length - 1] = L;
+  const U = new Float64Array(batch * N * L), sv = new Float64Array(batch * L), V = new Float64Array(batch * L * M);
+  addon.svdJac1(a, U, sv, V, batch, N, M);
+  return [new NDArray(uShape, U), new NDArray(sShape, sv), new NDArray(vShape, V)];
+}
+
+module.exports = {matmul2, matmul, cholesky_decomp, qr_decomp, svd_jac_1sided,
+                  init: d => addon.init(Int32Array.from(d || [])), stats: addon.stats,
+                  pinnedFloat64Array: addon.pinnedFloat64Array};
