@@ -294,6 +294,14 @@ def run_ours(args):
     del case
     torch.cuda.empty_cache()
 
+    if args.kernel_only:  # tuning aid: device-resident timing only, not a bench line
+        if rank == 0:
+            print(json.dumps({"workload": args.workload, "ms_per_launch": 1e3 * launch_s, "matrices_per_s": value,
+                              "gflops": value * flop_unit / 1e9, "hbm_gbs_algorithmic": achieved_gbs, "sweeps": sweeps}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---------------- end to end through the host-buffer C ABI ----------------
     call, h2d, d2h, keep = host_case(args.workload, nd, units)
     e2e_steps = max(1, min(args.steps, 10))
@@ -338,7 +346,15 @@ def run_ours(args):
         }
         if sweeps:
             line["sweeps"] = sweeps
-        line["fp64_peaks_measured"] = fp64_peaks(lib, local)
+        if args.fp64_probes:
+            line["fp64_peaks_measured"] = fp64_peaks(lib, local)
+        else:
+            try:
+                line["fp64_peaks_measured"] = {k: v for k, v in json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json"))).items()
+                                               if k.endswith("_peak_tflops") or k == "copy_gbs"}
+                line["fp64_peaks_measured"]["source"] = "profiles/r01_fp64_peak.json (tools/fp64_peak.py on this pool's B200)"
+            except Exception:
+                pass
 
     # ---------------- the other BASELINE configs, kernel-only, short ----------------
     if args.workload == "c2" and not args.no_others:
@@ -392,6 +408,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-others", action="store_true", help="skip the kernel-only lines of the other configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernel-only", action="store_true", help="tuning aid: print the device-resident timing only")
+    ap.add_argument("--fp64-probes", action="store_true", help="also measure the DFMA/DMMA pipe peaks (extra launches before the timed region)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,11 +13,12 @@
 //  * qr_generic_kernel : any shape; one CTA per matrix working in a global (L2-resident) scratch copy.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace nd4b {
 
 // Householder scalars for x = (x0, rest) with sigma = |rest|^2:  H = I - tau * v v^T, v = (1, rest/v0),
-// H x = (beta, 0), beta = ||x|| >= 0.
+// H x = (beta, 0), beta = ||x|| >= 0 (cancellation-free, dlarfgp style).  Used by the generic kernel.
 struct Reflector { double beta, tau, inv_v0; };
 
 __device__ __forceinline__ Reflector make_reflector(double x0, double sigma) {
@@ -28,8 +29,6 @@ __device__ __forceinline__ Reflector make_reflector(double x0, double sigma) {
     h.inv_v0 = 0.0;  // rest is all zero anyway
     return h;
   }
-  // scale-free norm: ||x|| = max * sqrt((x0/max)^2 + sigma/max^2) is not needed for |x| in a sane range;
-  // guard only against overflow/underflow of x0^2 + sigma
   double nrm = sqrt(fma(x0, x0, sigma));
   const double v0 = (x0 <= 0.0) ? (x0 - nrm) : (-sigma / (x0 + nrm));
   const double v0sq = v0 * v0;
@@ -39,18 +38,144 @@ __device__ __forceinline__ Reflector make_reflector(double x0, double sigma) {
   return h;
 }
 
+// The register kernel uses the classic (dlarfg) sign choice beta = -sign(x0)*||x||, which needs one rsqrt and
+// one reciprocal on the critical path instead of a sqrt and three divisions:
+//   v0 = x0 - beta = x0 + sign(x0)||x||,   tau = (beta - x0)/beta = 1 + |x0|/||x||.
+// Rows of R / columns of Q with beta < 0 are negated when they are stored, so that diag(R) >= 0 as documented.
+struct ReflectorS { double beta, tau, inv_v0; };
+
+__device__ __forceinline__ ReflectorS make_reflector_signed(double x0, double sigma) {
+  ReflectorS h;
+  const double s = fma(x0, x0, sigma);
+  if (s == 0.0) { h.beta = 0.0; h.tau = 0.0; h.inv_v0 = 0.0; return h; }
+  const double rn = rsqrt(s);
+  const double nrm = s * rn;
+  h.beta = -copysign(nrm, x0);
+  h.tau = fma(fabs(x0), rn, 1.0);
+  h.inv_v0 = 1.0 / (x0 - h.beta);
+  return h;
+}
+
 constexpr int kQrWarps = 4;
 
-__global__ void __launch_bounds__(kQrWarps * 32)
+// One Householder step on the register tile.  KB = k>>3 and E = k&1 are compile-time (they select registers),
+// ck = (k&7)>>1 is a run-time value: 8 code variants per phase instead of 32 keeps the kernel inside the
+// instruction cache.  a[i][jj]: row r+8i, column 8*(jj>>1) + 2c + (jj&1).
+template <int KB, int E, bool QPHASE>
+__device__ __forceinline__ void qr_step(double (&a)[8][8], int ck, int lane, int r, int c, double& mytau, double& mysgn) {
+  constexpr int i0 = KB, jk = 2 * KB + E;
+  const int k = 8 * KB + 2 * ck + E;
+  const int r0 = 2 * ck + E;               // row k lives in slot i0 of lanes with r == r0
+  const int src_c = (lane & ~3) | ck;      // same row group, owning column group
+  double tau, inv_v0 = 1.0;
+
+  if (!QPHASE) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = i0; i < 8; i++) {
+      const double x = a[i][jk];
+      const double xx = (i > i0 || r > r0) ? x : 0.0;
+      if ((i - i0) & 1) s1 = fma(xx, xx, s1); else s0 = fma(xx, xx, s0);
+    }
+    double ss = s0 + s1;
+    ss += shfl_xor(ss, 4);
+    ss += shfl_xor(ss, 8);
+    ss += shfl_xor(ss, 16);
+    const double sigma = shfl(ss, ck);
+    const double x0 = shfl(a[i0][jk], 4 * r0 + ck);
+    const ReflectorS h = make_reflector_signed(x0, sigma);
+    tau = h.tau;
+    inv_v0 = h.inv_v0;
+    if (lane == k) { mytau = h.tau; mysgn = (h.beta < 0.0) ? -1.0 : 1.0; }
+    if (c == ck && r == r0) a[i0][jk] = h.beta;
+  } else {
+    tau = shfl(mytau, k);
+  }
+
+  double vv[8];
+#pragma unroll
+  for (int i = i0; i < 8; i++) {
+    const double x = shfl(a[i][jk], src_c);
+    vv[i] = QPHASE ? x : x * inv_v0;
+  }
+  vv[i0] = (r > r0) ? vv[i0] : (r == r0 ? 1.0 : 0.0);
+  if (!QPHASE && c == ck) {
+#pragma unroll
+    for (int i = i0; i < 8; i++)
+      if (i > i0 || r > r0) a[i][jk] = vv[i];
+  }
+
+  // w_j = v^T A_j for the column slots that can hold columns > k, all slots interleaved (independent chains)
+  constexpr int J0 = 2 * KB, NJ = 8 - J0;
+  double w[NJ];
+  {
+    // two partial chains per column slot (even / odd row slots) halve the dependent-FMA depth
+    double w1[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { w[j] = vv[i0] * a[i0][J0 + j]; w1[j] = (i0 + 1 < 8) ? vv[(i0 + 1) & 7] * a[(i0 + 1) & 7][J0 + j] : 0.0; }
+#pragma unroll
+    for (int i = i0 + 2; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        if ((i - i0) & 1) w1[j] = fma(vv[i], a[i][J0 + j], w1[j]);
+        else w[j] = fma(vv[i], a[i][J0 + j], w[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < NJ; j++) w[j] += w1[j];
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; j++) w[j] += shfl_xor(w[j], 4);
+#pragma unroll
+  for (int j = 0; j < NJ; j++) w[j] += shfl_xor(w[j], 8);
+#pragma unroll
+  for (int j = 0; j < NJ; j++) w[j] += shfl_xor(w[j], 16);
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int jj = J0 + j;
+    const int col = 8 * (jj >> 1) + 2 * c + (jj & 1);
+    const double f = (col > k) ? -tau * w[j] : 0.0;
+#pragma unroll
+    for (int i = i0; i < 8; i++) a[i][jj] = fma(f, vv[i], a[i][jj]);
+  }
+
+  if (QPHASE && c == ck) {  // column k of Q: e_k - tau * v_k ; rows < k are zero
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int row = r + 8 * i;
+      double q = 0.0;
+      if (i >= i0) q = (row > k) ? -tau * vv[i] : (row == k ? 1.0 - tau : 0.0);
+      a[i][jk] = q;
+    }
+  }
+}
+
+template <int KB, bool QPHASE>
+__device__ __forceinline__ void qr_block(double (&a)[8][8], int lane, int r, int c, double& mytau, double& mysgn) {
+  if (!QPHASE) {
+#pragma unroll 1
+    for (int ck = 0; ck < 4; ck++) {
+      qr_step<KB, 0, false>(a, ck, lane, r, c, mytau, mysgn);
+      qr_step<KB, 1, false>(a, ck, lane, r, c, mytau, mysgn);
+    }
+  } else {
+#pragma unroll 1
+    for (int ck = 3; ck >= 0; ck--) {
+      qr_step<KB, 1, true>(a, ck, lane, r, c, mytau, mysgn);
+      qr_step<KB, 0, true>(a, ck, lane, r, c, mytau, mysgn);
+    }
+  }
+}
+
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 qr64x32_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch) {
   constexpr int ROWS = 64, COLS = 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, c = lane & 3;
-  const int64_t m = (int64_t)blockIdx.x * kQrWarps + warp;
+  const int64_t m = (int64_t)blockIdx.x * WARPS + warp;
   if (m >= batch) return;  // warp-uniform
   const double* a_in = A + m * (ROWS * COLS);
 
-  // a[i][jj]: row r+8i, column 8*(jj>>1) + 2c + (jj&1)
   double a[8][8];
 #pragma unroll
   for (int i = 0; i < 8; i++)
@@ -61,121 +186,45 @@ qr64x32_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __r
       a[i][2 * jp + 1] = v.y;
     }
 
-  double mytau = 0.0;  // lane k keeps tau_k
+  double mytau = 0.0, mysgn = 1.0;  // lane k keeps tau_k and the sign of beta_k
 
-  // ---------------- R phase ----------------
-#pragma unroll
-  for (int k = 0; k < COLS; k++) {
-    const int i0 = k >> 3, r0 = k & 7;          // row k lives in slot i0 of lanes with r == r0
-    const int ck = (k & 7) >> 1;                // column k lives in lanes with c == ck ...
-    const int jk = 2 * (k >> 3) + (k & 1);      // ... in register column jk
-    const int src_c = (lane & ~3) | ck;         // same row group, owning column group
+  qr_block<0, false>(a, lane, r, c, mytau, mysgn);
+  qr_block<1, false>(a, lane, r, c, mytau, mysgn);
+  qr_block<2, false>(a, lane, r, c, mytau, mysgn);
+  qr_block<3, false>(a, lane, r, c, mytau, mysgn);
 
-    double ss = 0.0;
-#pragma unroll
-    for (int i = i0; i < 8; i++) {
-      const double x = a[i][jk];
-      if (i > i0 || r > r0) ss = fma(x, x, ss);
-    }
-    ss += shfl_xor(ss, 4);
-    ss += shfl_xor(ss, 8);
-    ss += shfl_xor(ss, 16);
-    const double sigma = shfl(ss, ck);
-    const double x0 = shfl(a[i0][jk], 4 * r0 + ck);
-    const Reflector h = make_reflector(x0, sigma);
-    if (lane == k) mytau = h.tau;
-
-    double vv[8];
-#pragma unroll
-    for (int i = i0; i < 8; i++) {
-      const double x = shfl(a[i][jk], src_c);
-      vv[i] = x * h.inv_v0;
-    }
-    vv[i0] = (r > r0) ? vv[i0] : (r == r0 ? 1.0 : 0.0);
-    if (c == ck) {
-#pragma unroll
-      for (int i = i0; i < 8; i++)
-        if (i > i0 || r > r0) a[i][jk] = vv[i];
-      if (r == r0) a[i0][jk] = h.beta;
-    }
-
-    // trailing columns: slots jj >= 2*(k>>3) can hold columns > k
-#pragma unroll
-    for (int jj = 2 * (k >> 3); jj < 8; jj++) {
-      const int col = 8 * (jj >> 1) + 2 * c + (jj & 1);
-      double w = 0.0;
-#pragma unroll
-      for (int i = i0; i < 8; i++) w = fma(vv[i], a[i][jj], w);
-      w += shfl_xor(w, 4);
-      w += shfl_xor(w, 8);
-      w += shfl_xor(w, 16);
-      const double f = (col > k) ? h.tau * w : 0.0;
-#pragma unroll
-      for (int i = i0; i < 8; i++) a[i][jj] = fma(-f, vv[i], a[i][jj]);
-    }
-  }
-
-  // ---------------- store R (rows 0..31 are slots i < 4) ----------------
+  // ---------------- store R (rows 0..31 are slots i < 4), rows with beta < 0 negated ----------------
   {
     double* r_out = R + m * (COLS * COLS);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int row = r + 8 * i;
+      const double sg = shfl(mysgn, row);
 #pragma unroll
       for (int jp = 0; jp < 4; jp++) {
         const int col = 8 * jp + 2 * c;
-        const double x = (col >= row) ? a[i][2 * jp] : 0.0;
-        const double y = (col + 1 >= row) ? a[i][2 * jp + 1] : 0.0;
+        const double x = (col >= row) ? sg * a[i][2 * jp] : 0.0;
+        const double y = (col + 1 >= row) ? sg * a[i][2 * jp + 1] : 0.0;
         stg2_stream(r_out + row * COLS + col, x, y);
       }
     }
   }
 
-  // ---------------- Q phase: Q = H_0 ... H_31 [I;0], formed in place over the reflectors ----------------
-#pragma unroll
-  for (int k = COLS - 1; k >= 0; k--) {
-    const int i0 = k >> 3, r0 = k & 7;
-    const int ck = (k & 7) >> 1;
-    const int jk = 2 * (k >> 3) + (k & 1);
-    const int src_c = (lane & ~3) | ck;
-    const double tau = shfl(mytau, k);
-
-    double vv[8];
-#pragma unroll
-    for (int i = i0; i < 8; i++) vv[i] = shfl(a[i][jk], src_c);
-    vv[i0] = (r > r0) ? vv[i0] : (r == r0 ? 1.0 : 0.0);
-
-#pragma unroll
-    for (int jj = 2 * (k >> 3); jj < 8; jj++) {
-      const int col = 8 * (jj >> 1) + 2 * c + (jj & 1);
-      double w = 0.0;
-#pragma unroll
-      for (int i = i0; i < 8; i++) w = fma(vv[i], a[i][jj], w);
-      w += shfl_xor(w, 4);
-      w += shfl_xor(w, 8);
-      w += shfl_xor(w, 16);
-      const double f = (col > k) ? tau * w : 0.0;
-#pragma unroll
-      for (int i = i0; i < 8; i++) a[i][jj] = fma(-f, vv[i], a[i][jj]);
-    }
-    // column k of Q: e_k - tau * v_k ; rows < k are zero
-    if (c == ck) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int row = r + 8 * i;
-        double q = 0.0;
-        if (i >= i0) q = (row > k) ? -tau * vv[i] : (row == k ? 1.0 - tau : 0.0);
-        a[i][jk] = q;
-      }
-    }
-  }
+  // ---------------- Q = H_0 ... H_31 [I;0], formed in place over the reflectors ----------------
+  qr_block<3, true>(a, lane, r, c, mytau, mysgn);
+  qr_block<2, true>(a, lane, r, c, mytau, mysgn);
+  qr_block<1, true>(a, lane, r, c, mytau, mysgn);
+  qr_block<0, true>(a, lane, r, c, mytau, mysgn);
 
   double* q_out = Q + m * (ROWS * COLS);
+  double sg[8];
+#pragma unroll
+  for (int jj = 0; jj < 8; jj++) sg[jj] = shfl(mysgn, 8 * (jj >> 1) + 2 * c + (jj & 1));
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
     for (int jp = 0; jp < 4; jp++)
-      stg2_stream(q_out + (r + 8 * i) * COLS + 8 * jp + 2 * c, a[i][2 * jp], a[i][2 * jp + 1]);
+      stg2_stream(q_out + (r + 8 * i) * COLS + 8 * jp + 2 * c, sg[2 * jp] * a[i][2 * jp], sg[2 * jp + 1] * a[i][2 * jp + 1]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -282,9 +331,13 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
   const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q) |
                          reinterpret_cast<uintptr_t>(R)) & 15) == 0;
   if (rows == 64 && cols == 32 && aligned) {
-    const int64_t grid = (batch + kQrWarps - 1) / kQrWarps;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    qr64x32_kernel<<<(unsigned)grid, kQrWarps * 32, 0, s>>>(A, Q, R, batch);
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("ND4B_QR_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (batch > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if (variant == 1) qr64x32_kernel<1, 9><<<(unsigned)batch, 32, 0, s>>>(A, Q, R, batch);
+    else if (variant == 2) qr64x32_kernel<4, 3><<<(unsigned)((batch + 3) / 4), 128, 0, s>>>(A, Q, R, batch);
+    else if (variant == 3) qr64x32_kernel<2, 5><<<(unsigned)((batch + 1) / 2), 64, 0, s>>>(A, Q, R, batch);
+    else qr64x32_kernel<kQrWarps, 2><<<(unsigned)((batch + kQrWarps - 1) / kQrWarps), kQrWarps * 32, 0, s>>>(A, Q, R, batch);
     return cudaGetLastError();
   }
   const int L = rows < cols ? rows : cols;
