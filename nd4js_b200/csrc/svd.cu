@@ -108,15 +108,17 @@ constexpr size_t kSvd64Smem = sizeof(double) * (2 * 64 * kSvd64LD + 64) + sizeof
 // Shared tail of the 64x64 kernels.  On entry G (converged, columns mutually orthogonal) and the accumulated V are
 // column-major in shared memory (column stride LD); computes sigma, the stable descending order, U = G diag(1/sigma)
 // (zero columns completed to an orthonormal basis) and writes U, sv, V.  Called by all 256 threads after a barrier.
+template <int T>
 __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* sq, int* perm, int* zero_flag, int* done_flag,
                                                double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V, int64_t m) {
   constexpr int N = 64, LD = kSvd64LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NG = T / 8;  // 8-lane groups in the CTA; each handles columns P, P+NG, ...
   const int sub = lane & 7, P = warp * 4 + (lane >> 3);
-  // singular values: column norms (each 8-lane group handles columns P and P+32)
+  // singular values: column norms
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int col = P + 32 * h;
+  for (int h = 0; h < N / NG; h++) {
+    const int col = P + NG * h;
     const double2* g = reinterpret_cast<const double2*>(Gs + col * LD + 2 * sub);
     double a = 0.0;
 #pragma unroll
@@ -144,8 +146,8 @@ __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* s
   __syncthreads();
   // normalise the columns of G in place -> U columns
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int col = P + 32 * h;
+  for (int h = 0; h < N / NG; h++) {
+    const int col = P + NG * h;
     if (!zero_flag[col]) {
       const double sj = sq[col];
       double2* g = reinterpret_cast<double2*>(Gs + col * LD + 2 * sub);
@@ -163,7 +165,7 @@ __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* s
 
   double* u_out = U + m * (N * N);
   double* v_out = V + m * (N * N);
-  for (int e = tid; e < N * N; e += kSvd64Threads) {
+  for (int e = tid; e < N * N; e += T) {
     const int i = e >> 6, l = e & 63;
     u_out[e] = Gs[perm[l] * LD + i];   // U[i][l]
     v_out[e] = Vs[perm[i] * LD + l];   // V[l'][j] with l' = i, j = l
@@ -255,7 +257,7 @@ svd64_smem_kernel(const double* __restrict__ A, double* __restrict__ U, double* 
     if (!converged && fail_out) atomicExch(fail_out, 1);
   }
 
-  svd64_epilogue(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
+  svd64_epilogue<kSvd64Threads>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -299,37 +301,45 @@ __device__ __forceinline__ void rot_swap(double& xa, double& xb, double c, doubl
   xb = np;
 }
 
-// One odd-even step for all 256 threads.  STEP_B selects the slot pattern; pw is the parameter warp.
-template <bool STEP_B>
-__device__ __forceinline__ void svd64_step(double (&g)[16], double (&v)[16], double* dpart, double2* cs_now, double* nslot,
+// Recursive halving over the RL row-lanes of a warp: x[0..N) per lane -> x[0..N/RL) per lane, where lane rl ends
+// with the sums of elements rl*(N/RL) ... ; `mask` is the highest row-lane bit.
+template <int N, int STOP>
+__device__ __forceinline__ void halve_down(double (&x)[N], int rl, int mask) {
+  if constexpr (N > STOP) {
+    halve<N>(x, (rl & mask) != 0, mask);
+    double y[N / 2];
+#pragma unroll
+    for (int k = 0; k < N / 2; k++) y[k] = x[k];
+    halve_down<N / 2, STOP>(y, rl, mask >> 1);
+#pragma unroll
+    for (int k = 0; k < STOP; k++) x[k] = y[k];
+  }
+}
+
+// One odd-even step.  NQ = threads per matrix row (4: quarter rows, 256 threads; 2: half rows, 128 threads);
+// SL = 64/NQ slots per thread, RL = 32/NQ row-lanes per warp (lane = q*RL + rl), 2*NQ warps per matrix.
+// cs holds (c, s) of pair i = (SL/2)*q + j at index NQ*j + q, so that the NQ groups of a warp read adjacent words.
+template <int NQ, bool STEP_B>
+__device__ __forceinline__ void svd64_step(double (&g)[64 / NQ], double (&v)[64 / NQ], double* dpart, double2* cs_now, double* nslot,
                                            int* flags, int warp, int lane, int rl, int q, int pw, double tol2) {
-  constexpr int N = 64;
-  const bool b4 = rl & 4, b3 = rl & 2, b2 = rl & 1;
+  constexpr int N = 64, SL = 64 / NQ, NP = SL / 2, RL = 32 / NQ, NW = 2 * NQ;
   // ---- P1: the dot products of this step's pairs ----
-  double gR0 = 0.0, gL15 = 0.0, vR0 = 0.0, vL15 = 0.0;
-  double pd[8];
+  double gR0 = 0.0, gL = 0.0, vR0 = 0.0, vL = 0.0;
+  double pd[NP];
   if (!STEP_B) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) pd[j] = g[2 * j] * g[2 * j + 1];
+    for (int j = 0; j < NP; j++) pd[j] = g[2 * j] * g[2 * j + 1];
   } else {
-    gR0 = __shfl_down_sync(kFull, g[0], 8);   // lane + 8 = (rl, q + 1)
-    gL15 = __shfl_up_sync(kFull, g[15], 8);   // lane - 8 = (rl, q - 1)
-    vR0 = __shfl_down_sync(kFull, v[0], 8);
-    vL15 = __shfl_up_sync(kFull, v[15], 8);
+    gR0 = __shfl_down_sync(kFull, g[0], RL);       // lane + RL = (rl, q + 1)
+    gL = __shfl_up_sync(kFull, g[SL - 1], RL);     // lane - RL = (rl, q - 1)
+    vR0 = __shfl_down_sync(kFull, v[0], RL);
+    vL = __shfl_up_sync(kFull, v[SL - 1], RL);
 #pragma unroll
-    for (int j = 0; j < 7; j++) pd[j] = g[2 * j + 1] * g[2 * j + 2];
-    pd[7] = (q < 3) ? g[15] * gR0 : 0.0;
+    for (int j = 0; j < NP - 1; j++) pd[j] = g[2 * j + 1] * g[2 * j + 2];
+    pd[NP - 1] = (q < NQ - 1) ? g[SL - 1] * gR0 : 0.0;
   }
-  halve<8>(pd, b4, 4);
-  {
-    double h4[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) h4[k] = pd[k];
-    halve<4>(h4, b3, 2);
-    double h2[2] = {h4[0], h4[1]};
-    halve<2>(h2, b2, 1);
-    dpart[warp * 64 + 8 * q + rl] = h2[0];  // pair 8q + rl, rows of this warp
-  }
+  halve_down<NP, 1>(pd, rl, RL / 2);
+  dpart[warp * 64 + NP * q + rl] = pd[0];  // pair NP*q + rl, rows of this warp
   __syncthreads();  // B1
 
   // ---- P2: one lane per pair: threshold test, (c, s), cached-norm update ----
@@ -337,67 +347,73 @@ __device__ __forceinline__ void svd64_step(double (&g)[16], double (&v)[16], dou
     const int i = lane;
     double d = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) d += dpart[w * 64 + i];
+    for (int w = 0; w < NW; w++) d += dpart[w * 64 + i];
     const int sp = STEP_B ? 2 * i + 1 : 2 * i, sqq = sp + 1;
     const bool have = sqq < N;
     const double na = nslot[sp], nb = have ? nslot[sqq] : 0.0;
     double c = 1.0, s = 0.0;
     if (have && d * d > tol2 * na * nb) {
+      // theta from cos 2theta = |num|/h, sin 2theta = |den|/h (two rsqrt, no division):
+      //   c = sqrt((1 + c2)/2),  s = sign * s2 / (2c);  norms by the exact quadratic forms
       const double num = nb - na, den = 2.0 * d;
-      const double h = sqrt(fma(num, num, den * den));
-      double t = fabs(den) / (fabs(num) + h);
-      if ((num < 0.0) != (den < 0.0)) t = -t;
-      c = rsqrt(fma(t, t, 1.0));
-      s = c * t;
-      nslot[sp] = fmax(fma(t, d, nb), 0.0);  // exchanged: first slot now holds the rotated q column
-      nslot[sqq] = fmax(fma(-t, d, na), 0.0);
+      const double rh = rsqrt(fma(num, num, den * den));
+      const double c2 = fabs(num) * rh, s2 = fabs(den) * rh;
+      const double hc = fma(0.5, c2, 0.5);
+      const double rc = rsqrt(hc);
+      c = hc * rc;
+      s = 0.5 * s2 * rc;
+      if ((num < 0.0) != (den < 0.0)) s = -s;
+      const double cc = c * c, ss = s * s, csd = 2.0 * c * s * d;
+      nslot[sp] = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);   // exchanged: first slot now holds the rotated q column
+      nslot[sqq] = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);
       flags[0] = 1;
     } else if (have) {
       nslot[sp] = nb;
       nslot[sqq] = na;
     }
-    cs_now[4 * (i & 7) + (i >> 3)] = make_double2(c, s);
+    cs_now[NQ * (i % NP) + (i / NP)] = make_double2(c, s);
   }
   __syncthreads();  // B2
 
   // ---- rotate G and V with the same coefficients ----
   if (!STEP_B) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const double2 r = cs_now[4 * j + q];
+    for (int j = 0; j < NP; j++) {
+      const double2 r = cs_now[NQ * j + q];
       rot_swap(g[2 * j], g[2 * j + 1], r.x, r.y);
       rot_swap(v[2 * j], v[2 * j + 1], r.x, r.y);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-      const double2 r = cs_now[4 * j + q];
+    for (int j = 0; j < NP - 1; j++) {
+      const double2 r = cs_now[NQ * j + q];
       rot_swap(g[2 * j + 1], g[2 * j + 2], r.x, r.y);
       rot_swap(v[2 * j + 1], v[2 * j + 2], r.x, r.y);
     }
-    if (q < 3) {  // pair 8q+7 = (my slot 15, right neighbour's slot 0): first slot <- s p + c q
-      const double2 r = cs_now[28 + q];
-      g[15] = fma(r.y, g[15], r.x * gR0);
-      v[15] = fma(r.y, v[15], r.x * vR0);
+    if (q < NQ - 1) {  // pair NP*q + NP-1 = (my last slot, right neighbour's slot 0): first slot <- s p + c q
+      const double2 r = cs_now[NQ * (NP - 1) + q];
+      g[SL - 1] = fma(r.y, g[SL - 1], r.x * gR0);
+      v[SL - 1] = fma(r.y, v[SL - 1], r.x * vR0);
     }
-    if (q > 0) {  // pair 8q-1 = (left neighbour's slot 15, my slot 0): second slot <- c p - s q
-      const double2 r = cs_now[27 + q];
-      g[0] = fma(r.x, gL15, -(r.y * g[0]));
-      v[0] = fma(r.x, vL15, -(r.y * v[0]));
+    if (q > 0) {  // pair NP*q - 1 = (left neighbour's last slot, my slot 0): second slot <- c p - s q
+      const double2 r = cs_now[NQ * (NP - 1) + q - 1];
+      g[0] = fma(r.x, gL, -(r.y * g[0]));
+      v[0] = fma(r.x, vL, -(r.y * v[0]));
     }
   }
 }
 
-__global__ void __launch_bounds__(kSvd64Threads, 2)
+template <int NQ, int MINB>
+__global__ void __launch_bounds__(64 * NQ, MINB)
 svd64_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
              int64_t batch, int* sweeps_out, int* fail_out) {
-  constexpr int N = 64, LD = kSvd64LD;
+  constexpr int N = 64, LD = kSvd64LD, SL = 64 / NQ, RL = 32 / NQ, NW = 2 * NQ, T = 64 * NQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Gs = reinterpret_cast<double*>(smem_raw);
   double* Vs = Gs + N * LD;
   double* sq = Vs + N * LD;
-  double* dpart = sq + N;                                          // [8][64]
-  double2* cs = reinterpret_cast<double2*>(dpart + kSvdR_DPART);   // [2][32], index 4*(i&7) + (i>>3) for pair i
+  double* dpart = sq + N;                                          // [NW][64]
+  double2* cs = reinterpret_cast<double2*>(dpart + kSvdR_DPART);   // [2][32]
   double* nslot = reinterpret_cast<double*>(cs + 64);              // [64] cached |g_slot|^2
   int* perm = reinterpret_cast<int*>(nslot + N);
   int* zero_flag = perm + N;
@@ -407,18 +423,18 @@ svd64_kernel(const double* __restrict__ A, double* __restrict__ U, double* __res
   const int64_t m = blockIdx.x;
   if (m >= batch) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = lane >> 3, rl = lane & 7, row = 8 * warp + rl;    // quarter-major lanes: a quarter warp shares q
-  const double* a_in = A + m * (N * N) + row * N + 16 * q;
+  const int q = lane / RL, rl = lane % RL, row = RL * warp + rl;
+  const double* a_in = A + m * (N * N) + row * N + SL * q;
 
-  double g[16], v[16];
+  double g[SL], v[SL];
 #pragma unroll
-  for (int s = 0; s < 16; s += 2) {
+  for (int s = 0; s < SL; s += 2) {
     const double2 t = ldg2_stream(a_in + s);
     g[s] = t.x;
     g[s + 1] = t.y;
   }
 #pragma unroll
-  for (int s = 0; s < 16; s++) v[s] = (16 * q + s == row) ? 1.0 : 0.0;
+  for (int s = 0; s < SL; s++) v[s] = (SL * q + s == row) ? 1.0 : 0.0;
   if (tid == 0) flags[0] = 0;
 
   const double tol2 = (N * kEps) * (N * kEps);
@@ -428,33 +444,25 @@ svd64_kernel(const double* __restrict__ A, double* __restrict__ U, double* __res
     sweeps++;
     // ---- exact slot norms at the start of the sweep ----
     {
-      double n2[16];
+      double n2[SL];
 #pragma unroll
-      for (int s = 0; s < 16; s++) n2[s] = g[s] * g[s];
-      halve<16>(n2, rl & 4, 4);
-      double h8[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) h8[k] = n2[k];
-      halve<8>(h8, rl & 2, 2);
-      double h4[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) h4[k] = h8[k];
-      halve<4>(h4, rl & 1, 1);
-      dpart[warp * 64 + 16 * q + 2 * rl] = h4[0];  // slots 16q + 2rl + {0,1}
-      dpart[warp * 64 + 16 * q + 2 * rl + 1] = h4[1];
+      for (int s = 0; s < SL; s++) n2[s] = g[s] * g[s];
+      halve_down<SL, 2>(n2, rl, RL / 2);
+      dpart[warp * 64 + SL * q + 2 * rl] = n2[0];  // slots SL*q + 2rl + {0,1}
+      dpart[warp * 64 + SL * q + 2 * rl + 1] = n2[1];
       __syncthreads();
       if (tid < N) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) t += dpart[w * 64 + tid];
+        for (int w = 0; w < NW; w++) t += dpart[w * 64 + tid];
         nslot[tid] = t;
       }
       __syncthreads();
     }
 #pragma unroll 1
     for (int sp2 = 0; sp2 < N / 2; sp2++) {
-      svd64_step<false>(g, v, dpart, cs, nslot, flags, warp, lane, rl, q, (2 * sp2) & 7, tol2);
-      svd64_step<true>(g, v, dpart, cs + 32, nslot, flags, warp, lane, rl, q, (2 * sp2 + 1) & 7, tol2);
+      svd64_step<NQ, false>(g, v, dpart, cs, nslot, flags, warp, lane, rl, q, (2 * sp2) % NW, tol2);
+      svd64_step<NQ, true>(g, v, dpart, cs + 32, nslot, flags, warp, lane, rl, q, (2 * sp2 + 1) % NW, tol2);
     }
     __syncthreads();
     converged = (flags[0] == 0);
@@ -468,12 +476,178 @@ svd64_kernel(const double* __restrict__ A, double* __restrict__ U, double* __res
 
   // ---- registers -> column-major shared memory, then the common epilogue ----
 #pragma unroll
-  for (int s = 0; s < 16; s++) {
-    Gs[(16 * q + s) * LD + row] = g[s];
-    Vs[(16 * q + s) * LD + row] = v[s];
+  for (int s = 0; s < SL; s++) {
+    Gs[(SL * q + s) * LD + row] = g[s];
+    Vs[(SL * q + s) * LD + row] = v[s];
   }
   __syncthreads();
-  svd64_epilogue(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
+  svd64_epilogue<T>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64x64, register-resident, decoupled: warps 0-3 own G (half rows), warps 4-7 own V (half rows).
+// Only the G warps are on the critical path of a step (dot products -> parameters -> rotate G); the V warps
+// consume the (c, s) of each step from a two-deep ring in shared memory and apply them one or two steps later,
+// filling the FP64 pipe while the G warps wait on shuffles, rsqrt latency and their own barriers.
+// Hand-shakes use named hardware barriers (bar.sync / bar.arrive):
+//   id 1, 2 : G-internal (partials visible / parameters visible), 128 threads
+//   id 3, 4 : ring slot 0/1 "ready"  (128 G threads arrive, 128 V threads wait), 256
+//   id 5, 6 : ring slot 0/1 "free"   (128 V threads arrive, 128 G threads wait), 256
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <bool STEP_B>
+__device__ __forceinline__ void rotate_half(double (&x)[32], const double2* cs_slot, int q, int lane) {
+  // half-row layout: lane = 16q + rl, slots 32q .. 32q+31; pair i = 16q + j at cs index 2j + q
+  if (!STEP_B) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) { const double2 r = cs_slot[2 * j + q]; rot_swap(x[2 * j], x[2 * j + 1], r.x, r.y); }
+  } else {
+    const double xR0 = __shfl_down_sync(kFull, x[0], 16);
+    const double xL = __shfl_up_sync(kFull, x[31], 16);
+#pragma unroll
+    for (int j = 0; j < 15; j++) { const double2 r = cs_slot[2 * j + q]; rot_swap(x[2 * j + 1], x[2 * j + 2], r.x, r.y); }
+    if (q == 0) { const double2 r = cs_slot[30]; x[31] = fma(r.y, x[31], r.x * xR0); }        // pair 15 = (31 | 32)
+    else        { const double2 r = cs_slot[30]; x[0] = fma(r.x, xL, -(r.y * x[0])); }
+  }
+}
+
+template <bool STEP_B>
+__device__ __forceinline__ void svd64d_gstep(double (&g)[32], double* dpart, double2* cs_slot, double* nslot, int* flags,
+                                             int warp, int lane, int rl, int q, int pw, int slot, double tol2) {
+  constexpr int N = 64;
+  double pd[16];
+  if (!STEP_B) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) pd[j] = g[2 * j] * g[2 * j + 1];
+  } else {
+    const double gR0 = __shfl_down_sync(kFull, g[0], 16);
+#pragma unroll
+    for (int j = 0; j < 15; j++) pd[j] = g[2 * j + 1] * g[2 * j + 2];
+    pd[15] = (q == 0) ? g[31] * gR0 : 0.0;
+  }
+  halve_down<16, 1>(pd, rl, 8);
+  dpart[warp * 64 + 16 * q + rl] = pd[0];  // pair 16q + rl, rows of this warp
+  bar_sync(1, 128);
+  bar_sync(5 + slot, 256);                  // the V warps are done with this ring slot
+  if (warp == pw) {
+    const int i = lane;
+    const double d = (dpart[i] + dpart[64 + i]) + (dpart[128 + i] + dpart[192 + i]);
+    const int sp = STEP_B ? 2 * i + 1 : 2 * i, sqq = sp + 1;
+    const bool have = sqq < N;
+    const double na = nslot[sp], nb = have ? nslot[sqq] : 0.0;
+    double c = 1.0, s = 0.0;
+    if (have && d * d > tol2 * na * nb) {
+      const double num = nb - na, den = 2.0 * d;
+      const double rh = rsqrt(fma(num, num, den * den));
+      const double c2 = fabs(num) * rh, s2 = fabs(den) * rh;
+      const double hc = fma(0.5, c2, 0.5);
+      const double rc = rsqrt(hc);
+      c = hc * rc;
+      s = 0.5 * s2 * rc;
+      if ((num < 0.0) != (den < 0.0)) s = -s;
+      const double cc = c * c, ss = s * s, csd = 2.0 * c * s * d;
+      nslot[sp] = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);
+      nslot[sqq] = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);
+      flags[0] = 1;
+    } else if (have) {
+      nslot[sp] = nb;
+      nslot[sqq] = na;
+    }
+    cs_slot[2 * (i & 15) + (i >> 4)] = make_double2(c, s);
+  }
+  bar_sync(2, 128);
+  bar_arrive(3 + slot, 256);                // parameters of this step are published
+  rotate_half<STEP_B>(g, cs_slot, q, lane);
+}
+
+__global__ void __launch_bounds__(256, 2)
+svd64d_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
+              int64_t batch, int* sweeps_out, int* fail_out) {
+  constexpr int N = 64, LD = kSvd64LD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Gs = reinterpret_cast<double*>(smem_raw);
+  double* Vs = Gs + N * LD;
+  double* sq = Vs + N * LD;
+  double* dpart = sq + N;                                          // [4][64]
+  double2* cs = reinterpret_cast<double2*>(dpart + kSvdR_DPART);   // ring: [2][32]
+  double* nslot = reinterpret_cast<double*>(cs + 64);
+  int* perm = reinterpret_cast<int*>(nslot + N);
+  int* zero_flag = perm + N;
+  int* done_flag = zero_flag + N;
+  int* flags = done_flag + N;  // [0] rotated in this sweep, [1] continue flag for the V warps
+
+  const int64_t m = blockIdx.x;
+  if (m >= batch) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_g = warp < 4;
+  const int gw = warp & 3;                       // warp index inside its group
+  const int q = lane >> 4, rl = lane & 15, row = 16 * gw + rl;
+  double x[32];                                  // half a row of G (G warps) or of V (V warps)
+  if (is_g) {
+    const double* a_in = A + m * (N * N) + row * N + 32 * q;
+#pragma unroll
+    for (int s = 0; s < 32; s += 2) {
+      const double2 t = ldg2_stream(a_in + s);
+      x[s] = t.x;
+      x[s + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 32; s++) x[s] = (32 * q + s == row) ? 1.0 : 0.0;
+  }
+  if (tid == 0) { flags[0] = 0; flags[1] = 1; }
+  __syncthreads();
+
+  const double tol2 = (N * kEps) * (N * kEps);
+  int sweeps = 0;
+  bool converged = false;
+  while (sweeps < kMaxSweeps && !converged) {
+    sweeps++;
+    if (is_g) {
+      // exact slot norms at the start of the sweep (G warps only)
+      double n2[32];
+#pragma unroll
+      for (int s = 0; s < 32; s++) n2[s] = x[s] * x[s];
+      halve_down<32, 2>(n2, rl, 8);
+      dpart[gw * 64 + 32 * q + 2 * rl] = n2[0];
+      dpart[gw * 64 + 32 * q + 2 * rl + 1] = n2[1];
+      bar_sync(1, 128);
+      if (tid < N) nslot[tid] = (dpart[tid] + dpart[64 + tid]) + (dpart[128 + tid] + dpart[192 + tid]);
+      bar_sync(2, 128);
+#pragma unroll 1
+      for (int sp2 = 0; sp2 < N / 2; sp2++) {
+        svd64d_gstep<false>(x, dpart, cs, nslot, flags, gw, lane, rl, q, (2 * sp2) & 3, 0, tol2);
+        svd64d_gstep<true>(x, dpart, cs + 32, nslot, flags, gw, lane, rl, q, (2 * sp2 + 1) & 3, 1, tol2);
+      }
+    } else {
+      bar_arrive(5, 256);  // both ring slots start out free
+      bar_arrive(6, 256);
+#pragma unroll 1
+      for (int sp2 = 0; sp2 < N / 2; sp2++) {
+        bar_sync(3, 256);
+        rotate_half<false>(x, cs, q, lane);
+        if (sp2 + 1 < N / 2) bar_arrive(5, 256);
+        bar_sync(4, 256);
+        rotate_half<true>(x, cs + 32, q, lane);
+        if (sp2 + 1 < N / 2) bar_arrive(6, 256);
+      }
+    }
+    __syncthreads();
+    converged = (flags[0] == 0);
+    __syncthreads();
+    if (tid == 0) flags[0] = 0;
+  }
+  if (tid == 0) {
+    if (sweeps_out) atomicMax(sweeps_out, sweeps);
+    if (!converged && fail_out) atomicExch(fail_out, 1);
+  }
+  double* dst = is_g ? Gs : Vs;
+#pragma unroll
+  for (int s = 0; s < 32; s++) dst[(32 * q + s) * LD + row] = x[s];
+  __syncthreads();
+  svd64_epilogue<256>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,15 +804,22 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(svd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
+      cudaError_t e = cudaFuncSetAttribute(svd64_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64Smem);
       if (e != cudaSuccess) return e;
       attr_set[dev] = true;
     }
     static int variant = -1;
-    if (variant < 0) { const char* ev = getenv("ND4B_SVD_VARIANT"); variant = ev ? atoi(ev) : 0; }
+    if (variant < 0) {
+      const char* ev = getenv("ND4B_SVD_VARIANT");
+      variant = ev ? atoi(ev) : 0;
+    }
     if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else svd64_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    else if (variant == 3) svd64d_kernel<<<(unsigned)batch, 256, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    else if (variant == 2) svd64_kernel<2, 3><<<(unsigned)batch, 128, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    else svd64_kernel<4, 2><<<(unsigned)batch, 256, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     return cudaGetLastError();
   }
   const size_t need = svd_workspace_bytes(batch, rows, cols);
