@@ -36,6 +36,8 @@ WORKLOADS = {
     "c3": ("batched nd.la.cholesky_decomp float64 SPD [262144,16,16]", 262144, 4096, 16 ** 3 / 3.0),
     "c4": ("batched nd.la.qr_decomp float64 [65536,64,32] Householder", 65536, 40960, 2 * (2 * 64 * 32 * 32 - 2 * 32 ** 3 / 3.0)),
     "c5": ("batched nd.la.svd_jac_1sided float64 [16384,64,64]", 16384, 98816, 2016 * 1152),  # flop per sweep
+    # compute-bound probe of the same matmul kernel family (north_star: matmul vs FP64 tensor-core peak)
+    "g4k": ("nd.la.matmul float64 4096x4096 . 4096x4096 single matrix (compute-bound probe)", 1, 3 * 4096 * 4096 * 8, 2 * 4096 ** 3),
 }
 
 
@@ -106,7 +108,7 @@ def run_reference(args):
     nd4ref.build()
     desc, units, bpu, fpu = WORKLOADS[args.workload]
     rng = np.random.default_rng(3)
-    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24}[args.workload]
+    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24, "g4k": 1}[args.workload]
     fn, data = _ref_case(args.workload, sample, rng, nd4ref)
     for _ in range(min(args.warmup, 1)):
         fn(*data)
@@ -133,6 +135,8 @@ def _ref_case(name, n, rng, nd4ref):
     import numpy as np
     if name == "c1":
         return nd4ref.matmul2, (rng.uniform(-1, 1, (512, 512)), rng.uniform(-1, 1, (512, 512)))
+    if name == "g4k":
+        return nd4ref.matmul2, (rng.uniform(-1, 1, (4096, 4096)), rng.uniform(-1, 1, (4096, 4096)))
     if name == "c2":
         return nd4ref.matmul2, (rng.uniform(-1, 1, (n, 32, 32)), rng.uniform(-1, 1, (n, 32, 32)))
     if name == "c3":
@@ -154,8 +158,10 @@ class DeviceCase:
         u = lambda *s: torch.rand(*s, generator=g, **f64) * 2 - 1
         self.sweeps = None
         self.work = None
-        if name == "c1":
-            self.a, self.b, self.out = u(512, 512), u(512, 512), [torch.empty(512, 512, **f64)]
+        if name in ("c1", "g4k"):
+            n = 512 if name == "c1" else 4096
+            self.n = n
+            self.a, self.b, self.out = u(n, n), u(n, n), [torch.empty(n, n, **f64)]
         elif name == "c2":
             self.a, self.b, self.out = u(units, 32, 32), u(units, 32, 32), [torch.empty(units, 32, 32, **f64)]
         elif name == "c3":
@@ -176,8 +182,8 @@ class DeviceCase:
     def step(self, stream):
         L, p, d = self.lib, (lambda t: C.c_void_p(t.data_ptr())), self.dev
         s = C.c_void_p(stream)
-        if self.name == "c1":
-            rc = L.nd4b_dev_matmul_f64(d, s, p(self.a), 0, p(self.b), 0, p(self.out[0]), 1, 512, 512, 512)
+        if self.name in ("c1", "g4k"):
+            rc = L.nd4b_dev_matmul_f64(d, s, p(self.a), 0, p(self.b), 0, p(self.out[0]), 1, self.n, self.n, self.n)
         elif self.name == "c2":
             rc = L.nd4b_dev_matmul_f64(d, s, p(self.a), 1024, p(self.b), 1024, p(self.out[0]), self.units, 32, 32, 32)
         elif self.name == "c3":
@@ -219,8 +225,8 @@ def host_case(name, nd, units):
 
     L = nd.load()
     p = lambda t: C.c_void_p(t.data_ptr())
-    if name in ("c1", "c2"):
-        sh = (512, 512) if name == "c1" else (units, 32, 32)
+    if name in ("c1", "c2", "g4k"):
+        sh = (512, 512) if name == "c1" else (4096, 4096) if name == "g4k" else (units, 32, 32)
         a, b, c = pinned(sh, rng.uniform(-1, 1, sh)), pinned(sh, rng.uniform(-1, 1, sh)), pinned(sh)
         shp = np.asarray(sh, np.int32)
         sp = C.c_void_p(shp.ctypes.data)
@@ -335,11 +341,11 @@ def run_ours(args):
             "gflops": value * flop_unit / 1e9,
             "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timing": "host wall clock around the blocking C-ABI call, barrier+sync both sides, max over ranks",
-                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1"}[args.workload]},
+                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1"}[args.workload]},
             "gpu_launches": args.steps + int(e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": {"c1": "gemm_tiled_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
+                         "kernel": {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
                                     "c4": "qr64x32_kernel", "c5": "svd64_kernel"}[args.workload],
                          "algorithmic_bytes_per_unit": bpu, "units_per_launch": units},
             "clocks": clocks,
@@ -359,7 +365,7 @@ def run_ours(args):
     # ---------------- the other BASELINE configs, kernel-only, short ----------------
     if args.workload == "c2" and not args.no_others:
         others = {}
-        for name in ("c1", "c3", "c4", "c5"):
+        for name in ("c1", "g4k", "c3", "c4", "c5"):
             d2, u2, b2, f2 = WORKLOADS[name]
             c2 = DeviceCase(name, torch, lib, local, u2)
             barrier()
@@ -380,7 +386,7 @@ def run_ours(args):
         import numpy as np
         from oracle import nd4ref
         nd4ref.build()
-        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96}[args.workload]
+        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96, "g4k": 1}[args.workload]
         fn, data = _ref_case(args.workload, sample, np.random.default_rng(3), nd4ref)
         reps, t0 = 0, time.perf_counter()
         while True:

@@ -10,6 +10,7 @@
 // componentwise to a few ulp of (|A||B|)_ij (tests/ state the bound), not bit for bit.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace nd4b {
 
@@ -254,6 +255,140 @@ gemm_tiled_kernel(const double* __restrict__ A, const double* __restrict__ B, do
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pipelined tiled GEMM for 16-byte-aligned operands with even K and J: the same CTA tiling and padded
+// smem layout as gemm_tiled_kernel, but tiles are brought in by cp.async (LDGSTS, 16 bytes, zero-fill past
+// the edges) through a STAGES-deep ring, so global latency is hidden behind the DMMA stream instead of being
+// exposed at every k-tile.  This is the kernel behind the compute-bound figures (C1 and the large-N probes).
+// ------------------------------------------------------------------------------------------------
+template <int WR, int WC, int TM, int TN, int STAGES>
+struct PipeCfg {
+  static constexpr int BM = WR * TM * 8, BN = WC * TN * 8, BK = 16;
+  static constexpr int LDA = BK + 4, LDB = BN + 4;
+  static constexpr int THREADS = WR * WC * 32;
+  static constexpr int A_CHUNKS = BM * BK / 2, B_CHUNKS = BK * BN / 2;  // 16-byte chunks per tile
+  static constexpr int STAGE_DOUBLES = BM * LDA + BK * LDB;
+  static constexpr size_t SMEM = sizeof(double) * STAGES * STAGE_DOUBLES;
+  static_assert(BN % 16 == 0, "BN must be a multiple of 16");
+  static_assert(A_CHUNKS % THREADS == 0 && B_CHUNKS % THREADS == 0, "tile/threads mismatch");
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+template <int WR, int WC, int TM, int TN, int STAGES>
+__global__ void __launch_bounds__(WR * WC * 32)
+gemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                 int64_t batch, int I, int K, int J, BatchMap map, int tiles_m, int tiles_n) {
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, T = Cfg::THREADS;
+  extern __shared__ __align__(16) double gemm_smem[];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp / WC, wc = warp % WC;
+
+  int64_t tile = blockIdx.x;
+  const int tn = (int)(tile % tiles_n); tile /= tiles_n;
+  const int tm = (int)(tile % tiles_m); tile /= tiles_m;
+  const int64_t m = tile;
+  if (m >= batch) return;
+  int64_t ao, bo;
+  decode_batch(map, m, ao, bo);
+  const double* a = A + ao;
+  const double* b = B + bo;
+  double* c = C + m * (int64_t)I * J;
+  const int row0 = tm * BM, col0 = tn * BN;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(gemm_smem);
+
+  auto issue_tile = [&](int kt, int stage) {
+    const int k0 = kt * BK;
+    const uint32_t as = smem_base + (uint32_t)(stage * Cfg::STAGE_DOUBLES) * 8u;
+    const uint32_t bs = as + (uint32_t)(BM * LDA) * 8u;
+#pragma unroll
+    for (int i = 0; i < Cfg::A_CHUNKS / T; i++) {
+      const int ch = tid + i * T, r = ch / (BK / 2), kk = (ch % (BK / 2)) * 2;
+      const int gr = row0 + r, gk = k0 + kk;
+      const bool ok = gr < I && gk < K;
+      cp_async16(as + (uint32_t)(r * LDA + kk) * 8u, ok ? a + (int64_t)gr * K + gk : a, ok);
+    }
+#pragma unroll
+    for (int i = 0; i < Cfg::B_CHUNKS / T; i++) {
+      const int ch = tid + i * T, kk = ch / (BN / 2), cc = (ch % (BN / 2)) * 2;
+      const int gk = k0 + kk, gc = col0 + cc;
+      const bool ok = gk < K && gc < J;
+      cp_async16(bs + (uint32_t)(kk * LDB + cc) * 8u, ok ? b + (int64_t)gk * J + gc : b, ok);
+    }
+  };
+
+  double acc[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (K + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nk) issue_tile(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; kt++) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    __syncthreads();  // tile kt has landed for everybody; everybody is done with the stage refilled below
+    if (kt + STAGES - 1 < nk) issue_tile(kt + STAGES - 1, (kt + STAGES - 1) % STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* as = gemm_smem + (kt % STAGES) * Cfg::STAGE_DOUBLES + (wr * TM * 8 + g) * LDA + t;
+    const double* bs = gemm_smem + (kt % STAGES) * Cfg::STAGE_DOUBLES + BM * LDA + t * LDB + wc * TN * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double af[TM], bfr[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) af[i] = as[i * 8 * LDA + ks * 4];
+#pragma unroll
+      for (int j = 0; j < TN; j++) bfr[j] = bs[ks * 4 * LDB + j * 8];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bfr[j]);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    const int gr = row0 + (wr * TM + i) * 8 + g;
+    if (gr >= I) continue;
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+      const int gc = col0 + (wc * TN + j) * 8 + 2 * t;
+      if (gc < J) *reinterpret_cast<double2*>(c + (int64_t)gr * J + gc) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  }
+}
+
+template <int WR, int WC, int TM, int TN, int STAGES>
+static cudaError_t launch_pipe(cudaStream_t s, const double* A, const double* B, double* C,
+                               int64_t batch, int I, int K, int J, const BatchMap& map) {
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES>;
+  const int tiles_m = (I + Cfg::BM - 1) / Cfg::BM, tiles_n = (J + Cfg::BN - 1) / Cfg::BN;
+  const int64_t grid = batch * tiles_m * tiles_n;
+  if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  auto kern = gemm_pipe_kernel<WR, WC, TM, TN, STAGES>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(A, B, C, batch, I, K, J, map, tiles_m, tiles_n);
+  return cudaGetLastError();
+}
+
 template <int WR, int WC, int TM, int TN>
 static cudaError_t launch_tiled(cudaStream_t s, const double* A, const double* B, double* C,
                                 int64_t batch, int I, int K, int J, const BatchMap& map, bool vec) {
@@ -284,6 +419,22 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
   const bool vec = aligned && str_even && (K % 2 == 0) && (J % 2 == 0) && (((int64_t)I * J) % 2 == 0);
   // Tile choice: 64x64 tiles when they still give >= 2 CTAs per SM, else 64x32 (4 warps of 16x32) to
   // spread a single mid-sized product (e.g. 512^3 -> 128 CTAs) over the 148 SMs, else 16x16 per warp.
+  if (vec && K >= 64) {
+    // pipelined kernels: 128x128 tiles when they fill the machine, else 64x64, else 64x32 (e.g. one 512^3 -> 128 CTAs)
+    const int64_t t128 = batch * ((I + 127) / 128) * ((J + 127) / 128);
+    const int64_t t64 = batch * ((I + 63) / 64) * ((J + 63) / 64);
+    if (I >= 96 && J >= 96 && t128 >= sm_count) return launch_pipe<2, 4, 8, 4, 3>(s, A, B, C, batch, I, K, J, map);
+    if (I >= 48 && J >= 48 && t64 >= 2LL * sm_count) return launch_pipe<2, 2, 4, 4, 4>(s, A, B, C, batch, I, K, J, map);
+    if (I >= 48 && J >= 24) {
+      // few tiles (e.g. one 512^3 -> 128 CTAs): 8 warps of 16x16 per 64x32 tile keep two warps on every SM sub-partition
+      static int v = -1;
+      if (v < 0) { const char* e = getenv("ND4B_GEMM_SMALL"); v = e ? atoi(e) : 2; }
+      const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
+      if (v == 1 && t6432 < 2LL * sm_count) return launch_pipe<4, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
+      if (v == 2 && t6432 < 2LL * sm_count) return launch_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
+      return launch_pipe<4, 1, 2, 4, 4>(s, A, B, C, batch, I, K, J, map);
+    }
+  }
   const int64_t t6464 = batch * ((I + 63) / 64) * ((J + 63) / 64);
   const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
   if (I >= 48 && J >= 48 && t6464 >= 2LL * sm_count) return launch_tiled<2, 2, 4, 4>(s, A, B, C, batch, I, K, J, map, vec);
