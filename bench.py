@@ -273,6 +273,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nd.init([local])
     lib = nd.load()

@@ -104,6 +104,17 @@ int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, 
 int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
                       int64_t batch, int rows, int cols, int* sweeps_out);
 
+/* ---- nd.la.tril_solve / triu_solve (src/la/tri.js:156-293) and nd.la.cholesky_solve (src/la/cholesky.js:75-144) ---- */
+
+#define ND4B_TRIL_SOLVE     0   /* X = L^-1 Y, forward substitution  (_tril_solve, tri.js:45-71)          */
+#define ND4B_TRIU_SOLVE     1   /* X = U^-1 Y, backward substitution (_triu_solve, tri.js:73-98)          */
+#define ND4B_CHOLESKY_SOLVE 2   /* X = L^-T L^-1 Y                   (_tril_solve + _tril_t_solve)        */
+/* T[...,M,M], Y[...,M,J] -> X[...,M,J], leading dims broadcast like matmul2.  Bit-exact with the reference
+ * (same per-entry operation sequence).  Only the referenced triangle of T is read. */
+int nd4b_tri_solve_f64(int op, const double* T, const int32_t* t_shape, int t_ndim,
+                       const double* Y, const int32_t* y_shape, int y_ndim,
+                       double* X, const int32_t* x_shape, int x_ndim);
+
 /* ---- device-resident forms (inputs already in HBM; used for composition and kernel timing) --- */
 
 /* Batched C[m] = A[m*a_stride] . B[m*b_stride]; strides in ELEMENTS between consecutive matrices,

@@ -15,7 +15,7 @@ SYMBOLS = [
     "nd4b_host_alloc", "nd4b_host_free", "nd4b_set_chunk_bytes", "nd4b_get_stats", "nd4b_reset_stats",
     "nd4b_matmul_shape", "nd4b_matmul_f64", "nd4b_cholesky_f64", "nd4b_qr_f64", "nd4b_svd_jac1_f64",
     "nd4b_dev_matmul_f64", "nd4b_dev_cholesky_f64", "nd4b_dev_qr_f64", "nd4b_dev_svd_jac1_f64",
-    "nd4b_dev_qr_workspace", "nd4b_dev_svd_workspace", "nd4b_probe_fp64",
+    "nd4b_dev_qr_workspace", "nd4b_dev_svd_workspace", "nd4b_probe_fp64", "nd4b_tri_solve_f64",
 ]
 
 OK, E_SINGULAR = 0, 1
@@ -70,6 +70,7 @@ def load():
         "nd4b_dev_svd_jac1_f64": ([C.c_int, vp, dp, dp, dp, dp, i64, C.c_int, C.c_int, vp, dp, C.c_size_t], C.c_int),
         "nd4b_dev_qr_workspace": ([i64, C.c_int, C.c_int], C.c_size_t),
         "nd4b_dev_svd_workspace": ([i64, C.c_int, C.c_int], C.c_size_t),
+        "nd4b_tri_solve_f64": ([C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int], C.c_int),
         "nd4b_probe_fp64": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
     }
     for name, (args, res) in sig.items():

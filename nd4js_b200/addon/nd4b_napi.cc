@@ -118,6 +118,20 @@ napi_value SvdJac1(napi_env env, napi_callback_info info) {
   napi_value r; napi_create_int32(env, sweeps, &r); return r;
 }
 
+// triSolve(op, T, tShape, Y, yShape, X, xShape)   op 0 tril_solve, 1 triu_solve, 2 cholesky_solve
+napi_value TriSolve(napi_env env, napi_callback_info info) {
+  size_t argc = 7; napi_value v[7];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  int64_t op; F64 t, y, x; I32 ts, ys, xs;
+  if (argc < 7 || !get_int(env, v[0], &op) || !get_f64(env, v[1], &t) || !get_i32(env, v[2], &ts) || !get_f64(env, v[3], &y) ||
+      !get_i32(env, v[4], &ys) || !get_f64(env, v[5], &x) || !get_i32(env, v[6], &xs)) return nullptr;
+  if ((int64_t)t.n != prod(ts) || (int64_t)y.n != prod(ys) || (int64_t)x.n != prod(xs)) {
+    napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
+  }
+  if (nd4b_tri_solve_f64((int)op, t.p, ts.p, (int)ts.n, y.p, ys.p, (int)ys.n, x.p, xs.p, (int)xs.n)) return fail(env);
+  return undefined(env);
+}
+
 void free_pinned(napi_env, void* data, void*) { nd4b_host_free(data); }
 
 // pinnedFloat64Array(length) -> Float64Array backed by page-locked memory (skips the staging copy)
@@ -166,6 +180,7 @@ napi_value RegisterAll(napi_env env, napi_value exports) {
       {"matmul", nullptr, Matmul, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"cholesky", nullptr, Cholesky, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"qr", nullptr, Qr, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"triSolve", nullptr, TriSolve, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"svdJac1", nullptr, SvdJac1, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"pinnedFloat64Array", nullptr, PinnedFloat64Array, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"init", nullptr, Init, nullptr, nullptr, nullptr, napi_default, nullptr},

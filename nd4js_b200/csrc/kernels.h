@@ -26,6 +26,10 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
 cudaError_t launch_cholesky(cudaStream_t s, const double* S, double* L, int64_t batch, int n,
                             long long* info, long long base_index);
 
+// op 0 tril_solve, 1 triu_solve, 2 cholesky_solve; map.a_* addresses T (M*M per matrix), map.b_* addresses Y (M*J).
+cudaError_t launch_tri_solve(cudaStream_t s, int op, const double* T, const double* Y, double* X,
+                             int64_t batch, int M, int J, const BatchMap& map);
+
 size_t qr_workspace_bytes(int64_t batch, int rows, int cols);
 cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols,
                       double* work, size_t work_bytes);

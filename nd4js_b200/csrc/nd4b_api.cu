@@ -280,9 +280,9 @@ int build_batch_map(const int32_t* a_shape, int a_ndim, const int32_t* b_shape, 
                     const int32_t* c_shape, int c_ndim, BatchMap* map, bool* a_full, bool* b_full, int64_t* a_count,
                     int64_t* b_count) {
   const int nb = c_ndim - 2;
-  const int64_t I = a_shape[a_ndim - 2], K = a_shape[a_ndim - 1], J = b_shape[b_ndim - 1];
+  const int64_t a_el = (int64_t)a_shape[a_ndim - 2] * a_shape[a_ndim - 1], b_el = (int64_t)b_shape[b_ndim - 2] * b_shape[b_ndim - 1];
   std::vector<int64_t> size(nb), as(nb), bs(nb);
-  int64_t sa = I * K, sb = K * J;
+  int64_t sa = a_el, sb = b_el;
   *a_full = true;
   *b_full = true;
   for (int d = nb - 1; d >= 0; d--) {
@@ -296,8 +296,8 @@ int build_batch_map(const int32_t* a_shape, int a_ndim, const int32_t* b_shape, 
     sa *= na;
     sb *= nbb;
   }
-  *a_count = sa / (I * K);
-  *b_count = sb / (K * J);
+  *a_count = sa / a_el;
+  *b_count = sb / b_el;
   // merge adjacent dims when both operands stay affine: stride[d] == size[d+1]*stride[d+1]; drop size-1 dims
   std::vector<int64_t> ms, mas, mbs;
   for (int d = 0; d < nb; d++) {
@@ -601,6 +601,89 @@ int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
   if (sweeps_out) *sweeps_out = sweeps;
   if (failed) return fail(ND4B_E_NO_CONVERGENCE, "svd_jac_1sided: no convergence within the sweep limit (NaN or Inf in A?)");
   return ND4B_OK;
+}
+
+// ---- triangular solves ----------------------------------------------------------------------------
+
+int nd4b_tri_solve_f64(int op, const double* T, const int32_t* t_shape, int t_ndim,
+                       const double* Y, const int32_t* y_shape, int y_ndim,
+                       double* X, const int32_t* x_shape, int x_ndim) {
+  static const char* who[3] = {"tril_solve(L,Y)", "triu_solve(U,Y)", "cholesky_solve(L,y)"};
+  static const char* tn[3] = {"L", "U", "L"};
+  if (op < 0 || op > 2) return fail(ND4B_E_ARG, "tri_solve: op must be 0, 1 or 2");
+  if (!T || !Y || !X || !t_shape || !y_shape || !x_shape) return fail(ND4B_E_ARG, "%s: null pointer", who[op]);
+  if (t_ndim < 2) return fail(ND4B_E_A_NDIM, op == 2 ? "L must be at least 2D." : "%s: %s.ndim must be at least 2.", who[op], tn[op]);
+  if (y_ndim < 2) return fail(ND4B_E_B_NDIM, op == 2 ? "y must be at least 2D." : "%s: Y.ndim must be at least 2.", who[op]);
+  if (t_ndim > ND4B_MAX_NDIM || y_ndim > ND4B_MAX_NDIM) return fail(ND4B_E_ARG, "%s: ndim > %d", who[op], ND4B_MAX_NDIM);
+  for (int d = 0; d < t_ndim; d++) if (t_shape[d] < 1) return fail(ND4B_E_ARG, "Invalid shape: dims must be >= 1.");
+  for (int d = 0; d < y_ndim; d++) if (y_shape[d] < 1) return fail(ND4B_E_ARG, "Invalid shape: dims must be >= 1.");
+  const int M = y_shape[y_ndim - 2], J = y_shape[y_ndim - 1];
+  if (op == 2) {  // cholesky.js:84-85 checks squareness first
+    if (t_shape[t_ndim - 2] != t_shape[t_ndim - 1]) return fail(ND4B_E_NOT_SQUARE, "Last two dimensions of L must be quadratic.");
+    if (t_shape[t_ndim - 1] != M) return fail(ND4B_E_INNER, "L and y don't match.");
+  } else {
+    if (t_shape[t_ndim - 2] != M) return fail(ND4B_E_INNER, "%s: %s and Y don't match.", who[op], tn[op]);
+    if (t_shape[t_ndim - 1] != M) return fail(ND4B_E_NOT_SQUARE, "%s: Last two dimensions of %s must be quadratic.", who[op], tn[op]);
+  }
+  const int ndim = std::max(t_ndim, y_ndim);
+  int32_t want[ND4B_MAX_NDIM];
+  for (int d = 0; d < ndim; d++) want[d] = 1;
+  want[ndim - 2] = M;
+  want[ndim - 1] = J;
+  const int32_t* shp[2] = {t_shape, y_shape};
+  const int nds[2] = {t_ndim, y_ndim};
+  for (int w = 0; w < 2; w++)
+    for (int i = ndim - 2, j = nds[w] - 2; i-- > 0 && j-- > 0;) {
+      if (want[i] == 1) want[i] = shp[w][j];
+      else if (want[i] != shp[w][j] && shp[w][j] != 1)
+        return fail(ND4B_E_BROADCAST, op == 2 ? "Shapes are not broadcast-compatible." : "%s: %s and Y not broadcast-compatible.", who[op], tn[op]);
+    }
+  if (x_ndim != ndim) return fail(ND4B_E_SHAPE, "%s: result ndim %d, expected %d", who[op], x_ndim, ndim);
+  for (int d = 0; d < ndim; d++)
+    if (want[d] != x_shape[d]) return fail(ND4B_E_SHAPE, "%s: result shape mismatch at dim %d", who[op], d);
+
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  BatchMap map;
+  bool t_full, y_full;
+  int64_t t_count, y_count;
+  if (int rc = build_batch_map(t_shape, t_ndim, y_shape, y_ndim, x_shape, ndim, &map, &t_full, &y_full, &t_count, &y_count)) return rc;
+  int64_t batch = 1;
+  for (int d = 0; d < ndim - 2; d++) batch *= x_shape[d];
+  const int64_t t_elems = (int64_t)M * M, y_elems = (int64_t)M * J;
+  std::vector<Stream1> ins, outs;
+  int t_slot = -1, y_slot = -1;
+  if (t_full) { t_slot = (int)ins.size(); ins.push_back({T, nullptr, t_elems}); }
+  if (y_full) { y_slot = (int)ins.size(); ins.push_back({Y, nullptr, y_elems}); }
+  outs.push_back({nullptr, X, y_elems});
+  for (auto& dev : ctx->devs) {
+    CU(cudaSetDevice(dev.id));
+    if (!t_full) {
+      const size_t bytes = (size_t)t_count * t_elems * 8;
+      if (int rc = ensure_resident(dev, 0, bytes)) return rc;
+      CU(cudaMemcpyAsync(dev.resident[0], T, bytes, cudaMemcpyHostToDevice, dev.slots[0].stream));
+      ctx->h2d += bytes;
+    }
+    if (!y_full) {
+      const size_t bytes = (size_t)y_count * y_elems * 8;
+      if (int rc = ensure_resident(dev, 1, bytes)) return rc;
+      CU(cudaMemcpyAsync(dev.resident[1], Y, bytes, cudaMemcpyHostToDevice, dev.slots[0].stream));
+      ctx->h2d += bytes;
+    }
+    if (!t_full || !y_full) CU(cudaStreamSynchronize(dev.slots[0].stream));
+  }
+  auto launch = [&](const ChunkArgs& a) -> int {
+    BatchMap mm = map;
+    mm.base = a.base;
+    mm.a_lin = t_full ? t_elems : (t_count == 1 ? 0 : -1);
+    mm.b_lin = y_full ? y_elems : (y_count == 1 ? 0 : -1);
+    const double* tp = t_full ? a.in[t_slot] : static_cast<const double*>(a.dev->resident[0]);
+    const double* yp = y_full ? a.in[y_slot] : static_cast<const double*>(a.dev->resident[1]);
+    return check_cuda_launch(nd4b::launch_tri_solve(a.stream, op, tp, yp, a.out[0], a.count, M, J, mm), ctx);
+  };
+  return run_pipeline(ctx, batch, ins, outs, 0, launch);
 }
 
 // ---- device-resident forms ----------------------------------------------------------------------

@@ -102,6 +102,23 @@ function svd_jac_1sided(A) {
   return [new NDArray(uShape, U), new NDArray(sShape, sv), new NDArray(vShape, V)];
 }
 
-module.exports = {matmul2, matmul, cholesky_decomp, qr_decomp, svd_jac_1sided,
+// tril_solve / triu_solve (tri.js:156-293) and cholesky_solve (cholesky.js:75-144): op 0 / 1 / 2
+function triSolve(op, T, Y, errT, errY) {
+  T = asarray(T); if (T.ndim < 2) throw new Error(errT);
+  Y = asarray(Y); if (Y.ndim < 2) throw new Error(errY);
+  const ndim = Math.max(T.ndim, Y.ndim), xShape = new Int32Array(ndim).fill(1);
+  xShape[ndim - 2] = Y.shape[Y.ndim - 2]; xShape[ndim - 1] = Y.shape[Y.ndim - 1];
+  for (const shp of [T.shape, Y.shape])
+    for (let i = ndim - 2, j = shp.length - 2; i-- > 0 && j-- > 0;)
+      if (xShape[i] === 1) xShape[i] = shp[j];   // a mismatch is reported by the library with the reference's text
+  const X = new Float64Array(xShape.reduce((a, b) => a * b, 1));
+  addon.triSolve(op, f64(T, 'tri_solve'), T.shape, f64(Y, 'tri_solve'), Y.shape, X, xShape);
+  return new NDArray(xShape, X);
+}
+const tril_solve = (L, Y) => triSolve(0, L, Y, 'tril_solve(L,Y): L.ndim must be at least 2.', 'tril_solve(L,Y): Y.ndim must be at least 2.');
+const triu_solve = (U, Y) => triSolve(1, U, Y, 'triu_solve(U,Y): U.ndim must be at least 2.', 'triu_solve(U,Y): Y.ndim must be at least 2.');
+const cholesky_solve = (L, y) => triSolve(2, L, y, 'L must be at least 2D.', 'y must be at least 2D.');
+
+module.exports = {matmul2, matmul, cholesky_decomp, qr_decomp, svd_jac_1sided, tril_solve, triu_solve, cholesky_solve,
                   init: d => addon.init(Int32Array.from(d || [])), stats: addon.stats,
                   pinnedFloat64Array: addon.pinnedFloat64Array};

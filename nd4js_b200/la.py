@@ -5,6 +5,9 @@ Same names, argument meaning, result shapes and error texts as the reference:
   cholesky_decomp(S)                   src/la/cholesky.js:50-72
   qr_decomp(A) -> (Q,R)                src/la/qr.js:80-145
   svd_jac_1sided(A) -> (U,sv,V)        contract of src/la/svd_jac_2sided.js:30-144 (new export)
+  tril_solve(L,Y), triu_solve(U,Y)     src/la/tri.js:156-293
+  cholesky_solve(L,y)                  src/la/cholesky.js:75-144
+  qr_lstsq(Q,R,y) / qr_lstsq((Q,R),y)  src/la/qr.js:186-273
 Argument handling (asarray, upcasts, shape checks) stays on the host as it stays in JS in the
 reference; all arithmetic happens in libnd4b.so on the GPU.  Float64 only: other result dtypes raise
 (the reference's int32/float32/complex paths are outside the hot path and there is no CPU fallback).
@@ -166,3 +169,75 @@ def svd_jac_1sided(A):
     _lib.check(_lib.load().nd4b_svd_jac1_f64(_ptr(ad), _ptr(u), _ptr(sv), _ptr(v), ad.size // (rows * cols), rows, cols,
                                              C.byref(sweeps)))
     return NDArray(u_shape, u), NDArray(s_shape, sv), NDArray(v_shape, v)
+
+
+def _tri_solve(op, T, Y, err_t, err_y):
+    T, Y = asarray(T), asarray(Y)
+    if T.ndim < 2:
+        raise ValueError(err_t)
+    if Y.ndim < 2:
+        raise ValueError(err_y)
+    td, yd = _f64(T, "tri_solve"), _f64(Y, "tri_solve")
+    L = _lib.load()
+    t_s = np.ascontiguousarray(T.shape, np.int32)
+    y_s = np.ascontiguousarray(Y.shape, np.int32)
+    ndim = max(T.ndim, Y.ndim)
+    try:
+        lead = np.broadcast_shapes(tuple(T.shape[:-2]), tuple(Y.shape[:-2]))
+    except ValueError:
+        lead = (1,) * (ndim - 2)  # let the library produce the reference's error text
+    x_s = np.array(tuple(lead) + (int(Y.shape[-2]), int(Y.shape[-1])), np.int32)
+    x = _new(x_s)
+    rc = L.nd4b_tri_solve_f64(op, _ptr(td), _ptr(t_s), T.ndim, _ptr(yd), _ptr(y_s), Y.ndim, _ptr(x), _ptr(x_s), ndim)
+    if rc in (_lib.E_INNER, _lib.E_NOT_SQUARE, _lib.E_BROADCAST, _lib.E_A_NDIM, _lib.E_B_NDIM):
+        raise ValueError(_lib.last_error())
+    _lib.check(rc)
+    return NDArray(x_s, x)
+
+
+def tril_solve(L, Y):
+    return _tri_solve(0, L, Y, "tril_solve(L,Y): L.ndim must be at least 2.", "tril_solve(L,Y): Y.ndim must be at least 2.")
+
+
+def triu_solve(U, Y):
+    return _tri_solve(1, U, Y, "triu_solve(U,Y): U.ndim must be at least 2.", "triu_solve(U,Y): Y.ndim must be at least 2.")
+
+
+def cholesky_solve(L, y):
+    return _tri_solve(2, L, y, "L must be at least 2D.", "y must be at least 2D.")
+
+
+def qr_lstsq(Q, R, y=None):
+    """x = argmin |Q R x - y|: Q^T y on the GPU GEMM path, then the bit-exact back substitution.
+    The reference accumulates Q^T y sequentially (qr.js:246-249); the GEMM's rounding differs by a few ulp."""
+    if y is None:
+        y = R
+        Q, R = Q
+    Q, R, y = asarray(Q), asarray(R), asarray(y)
+    if Q.ndim < 2:
+        raise ValueError("qr_lstsq(Q,R,y): Q.ndim must be at least 2.")
+    if R.ndim < 2:
+        raise ValueError("qr_lstsq(Q,R,y): R.ndim must be at least 2.")
+    if y.ndim < 2:
+        raise ValueError("qr_lstsq(Q,R,y): y.ndim must be at least 2.")
+    n, m = int(Q.shape[-2]), int(Q.shape[-1])
+    i_, j_ = int(R.shape[-1]), int(y.shape[-1])
+    l = min(m, i_)
+    if n != int(y.shape[-2]):
+        raise ValueError("qr_lstsq(Q,R,y): Q and y don't match.")
+    if m != int(R.shape[-2]):
+        raise ValueError("qr_lstsq(Q,R,y): Q and R don't match.")
+    if i_ > n:
+        raise ValueError("qr_lstsq(Q,R,y): Under-determined systems not supported. Use rrqr instead.")
+    try:
+        np.broadcast_shapes(tuple(Q.shape[:-2]), tuple(R.shape[:-2]), tuple(y.shape[:-2]))
+    except ValueError:
+        raise ValueError("Q, R, y are not broadcast-compatible.")
+    qty = matmul2(Q.T, y).numpy()                                   # [..., m, j]
+    r = R.numpy()
+    x_top = triu_solve(np.ascontiguousarray(r[..., :l, :l]), np.ascontiguousarray(qty[..., :l, :])).numpy()
+    if l == i_:
+        return NDArray(np.asarray(x_top.shape, np.int32), x_top.reshape(-1))
+    x = np.zeros(x_top.shape[:-2] + (i_, j_))
+    x[..., :l, :] = x_top
+    return NDArray(np.asarray(x.shape, np.int32), x.reshape(-1))

@@ -440,6 +440,86 @@ int nd4ref_svd_jac2_f64(const double* A, double* U, double* sv, double* V,
   return rc;
 }
 
+/* ---------------------------------------------------------------- solves ----- */
+
+/* src/la/tri.js:45-71 (_tril_solve), :73-98 (_triu_solve), :100-125 (_tril_t_solve); M rows, N = row stride of T, O rhs columns */
+static void tril_solve1(int M, int N, int O, const double* L, double* X) {
+  for (int i = 0; i < M; i++) {
+    for (int k = 0; k < i; k++)
+      for (int j = 0; j < O; j++) X[O * i + j] -= L[N * i + k] * X[O * k + j];
+    for (int j = 0; j < O; j++) X[O * i + j] /= L[N * i + i];
+  }
+}
+static void triu_solve1(int M, int N, int O, const double* U, double* X) {
+  for (int i = M; i-- > 0;)
+    for (int j = O; j-- > 0;) {
+      for (int k = M; --k > i;) X[O * i + j] -= U[N * i + k] * X[O * k + j];
+      X[O * i + j] /= U[N * i + i];
+    }
+}
+static void tril_t_solve1(int M, int N, int O, const double* L, double* X) {
+  for (int k = M; k-- > 0;) {
+    for (int j = O; j-- > 0;) X[O * k + j] /= L[N * k + k];
+    for (int i = k; i-- > 0;)
+      for (int j = O; j-- > 0;) X[O * i + j] -= L[N * k + i] * X[O * k + j];
+  }
+}
+
+/* op 0: tril_solve (tri.js:156-230), 1: triu_solve (:233-293), 2: cholesky_solve (cholesky.js:75-144).
+ * T[...,M,M], Y[...,M,J] -> X[...,M,J], leading dims broadcast as in the reference's solv() recursion. */
+int nd4ref_tri_solve_f64(int op, const double* T, const int32_t* t_shape, int t_ndim,
+                         const double* Y, const int32_t* y_shape, int y_ndim,
+                         double* X, const int32_t* x_shape, int x_ndim) {
+  if (t_ndim < 2 || y_ndim < 2 || t_ndim > 64 || y_ndim > 64) return ND4REF_E_A_NDIM;
+  const int M = y_shape[y_ndim - 2], J = y_shape[y_ndim - 1];
+  if (t_shape[t_ndim - 2] != M) return ND4REF_E_INNER;
+  if (t_shape[t_ndim - 1] != M) return ND4REF_E_NOT_SQUARE;
+  const int ndim = t_ndim > y_ndim ? t_ndim : y_ndim;
+  if (x_ndim != ndim) return ND4REF_E_SHAPE;
+  int32_t want[64];
+  for (int d = 0; d < ndim; d++) want[d] = 1;
+  want[ndim - 2] = M;
+  want[ndim - 1] = J;
+  const int32_t* shp[2] = {t_shape, y_shape};
+  const int nd[2] = {t_ndim, y_ndim};
+  for (int w = 0; w < 2; w++)
+    for (int i = ndim - 2, j = nd[w] - 2; i-- > 0 && j-- > 0;) {
+      if (want[i] == 1) want[i] = shp[w][j];
+      else if (want[i] != shp[w][j] && shp[w][j] != 1) return ND4REF_E_BROADCAST;
+    }
+  for (int d = 0; d < ndim; d++)
+    if (want[d] != x_shape[d]) return ND4REF_E_SHAPE;
+  const int nb = ndim - 2;
+  int64_t t_str[64], y_str[64], idx[64], total = 1;
+  {
+    int64_t st = (int64_t)M * M, sy = (int64_t)M * J;
+    for (int d = nb - 1; d >= 0; d--) {
+      const int dt = d - ndim + t_ndim, dy = d - ndim + y_ndim;
+      const int64_t nt = dt >= 0 ? t_shape[dt] : 1, ny = dy >= 0 ? y_shape[dy] : 1;
+      t_str[d] = nt > 1 ? st : 0;
+      y_str[d] = ny > 1 ? sy : 0;
+      st *= nt;
+      sy *= ny;
+      idx[d] = 0;
+      total *= x_shape[d];
+    }
+  }
+  for (int64_t m = 0; m < total; m++) {
+    int64_t to = 0, yo = 0;
+    for (int d = 0; d < nb; d++) { to += idx[d] * t_str[d]; yo += idx[d] * y_str[d]; }
+    double* x = X + m * (int64_t)M * J;
+    memcpy(x, Y + yo, sizeof(double) * (size_t)M * J);
+    if (op == 0) tril_solve1(M, M, J, T + to, x);
+    else if (op == 1) triu_solve1(M, M, J, T + to, x);
+    else { tril_solve1(M, M, J, T + to, x); tril_t_solve1(M, M, J, T + to, x); }
+    for (int d = nb - 1; d >= 0; d--) {
+      if (++idx[d] < x_shape[d]) break;
+      idx[d] = 0;
+    }
+  }
+  return ND4REF_OK;
+}
+
 /* ------------------------------------------------------------------- norm ----- */
 
 /* src/la/norm.js:22-68 (FrobeniusNorm.include / result) */

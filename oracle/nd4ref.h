@@ -61,6 +61,12 @@ int nd4ref_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows
 int nd4ref_svd_jac2_f64(const double* A, double* U, double* sv, double* V,
                         int64_t batch, int rows, int cols, int* sweeps_out);
 
+/* tril_solve / triu_solve (src/la/tri.js:156-293) and cholesky_solve (src/la/cholesky.js:75-144):
+ * op 0, 1, 2.  T[...,M,M], Y[...,M,J] -> X[...,M,J] with broadcast leading dims. */
+int nd4ref_tri_solve_f64(int op, const double* T, const int32_t* t_shape, int t_ndim,
+                         const double* Y, const int32_t* y_shape, int y_ndim,
+                         double* X, const int32_t* x_shape, int x_ndim);
+
 /* scalar helpers exposed for unit tests */
 void nd4ref_giv_rot_qr(double a, double b, double out_c_s_norm[3]);      /* _giv_rot.js:22-37   */
 void nd4ref_svd_jac_angles(double Spp, double Spq, double Sqp, double Sqq,

@@ -48,6 +48,8 @@ def lib():
         L.nd4ref_cholesky_f64.argtypes = [dp, dp, i64, C.c_int, C.POINTER(i64)]
         L.nd4ref_qr_f64.argtypes = [dp, dp, dp, i64, C.c_int, C.c_int]
         L.nd4ref_svd_jac2_f64.argtypes = [dp, dp, dp, dp, i64, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.nd4ref_tri_solve_f64.argtypes = [C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int]
+        L.nd4ref_tri_solve_f64.restype = C.c_int
         L.nd4ref_giv_rot_qr.argtypes = [C.c_double, C.c_double, dp]
         L.nd4ref_svd_jac_angles.argtypes = [C.c_double] * 4 + [dp]
         L.nd4ref_frobenius.argtypes = [dp, i64]
@@ -136,6 +138,46 @@ def svd_jac_2sided(a, return_sweeps=False):
     if rc:
         raise RefError(rc)
     return (u, sv, v, sw.value) if return_sweeps else (u, sv, v)
+
+
+def _tri_solve(op, t, y):
+    t, y = _f64(t), _f64(y)
+    lead = np.broadcast_shapes(t.shape[:-2], y.shape[:-2])
+    x = np.empty(lead + y.shape[-2:], np.float64)
+    t_s, y_s, x_s = (np.asarray(a.shape, np.int32) for a in (t, y, x))
+    rc = lib().nd4ref_tri_solve_f64(op, _dp(t), _ip(t_s), t.ndim, _dp(y), _ip(y_s), y.ndim, _dp(x), _ip(x_s), x.ndim)
+    if rc:
+        raise RefError(rc)
+    return x
+
+
+def tril_solve(l, y):
+    return _tri_solve(0, l, y)
+
+
+def triu_solve(u, y):
+    return _tri_solve(1, u, y)
+
+
+def cholesky_solve(l, y):
+    return _tri_solve(2, l, y)
+
+
+def qr_lstsq(q, r, y):
+    """src/la/qr.js:186-273: x = triu_solve(R, Q^T y) with Q^T y accumulated k-ascending from 0, unfused."""
+    q, r, y = _f64(q), _f64(r), _f64(y)
+    n, m = q.shape[-2:]
+    i_, j_ = r.shape[-1], y.shape[-1]
+    l = min(m, i_)
+    lead = np.broadcast_shapes(q.shape[:-2], r.shape[:-2], y.shape[:-2])
+    qb, rb, yb = (np.broadcast_to(a, lead + a.shape[-2:]) for a in (q, r, y))
+    x = np.zeros(lead + (i_, j_))
+    for ix in np.ndindex(*lead):
+        qy = np.zeros((l, j_))
+        for k in range(n):  # x[i][j] += Q[k][i] * y[k][j], k ascending (qr.js:246-249)
+            qy += qb[ix][k, :l, None] * yb[ix][k][None, :]
+        x[ix][:l] = _tri_solve(1, np.ascontiguousarray(rb[ix][:l, :l]), qy)
+    return x
 
 
 def giv_rot_qr(a, b):

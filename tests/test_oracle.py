@@ -197,3 +197,28 @@ def test_frobenius(ref):
     x = uniform(0, (1000,))
     assert abs(ref.frobenius(x) - np.linalg.norm(x)) <= 1e-13 * np.linalg.norm(x)
     assert ref.frobenius(np.zeros(4)) == 0.0
+
+
+@pytest.mark.parametrize("op", ["tril_solve", "triu_solve", "cholesky_solve"])
+def test_tri_solves_vs_numpy(ref, op):
+    # cholesky_test.js:33-69 (2048 broadcast cholesky_solve cases) in miniature, plus tri.js public solves
+    rng = np.random.default_rng(len(op))
+    for _ in range(40):
+        m, j = (int(v) for v in rng.integers(1, 12, 2))
+        lead_t = [int(v) for v in rng.integers(1, 4, rng.integers(0, 3))]
+        lead_y = [d if rng.random() < 0.6 else 1 for d in lead_t][-int(rng.integers(0, 3)):] if lead_t else []
+        t = rng.uniform(-1, 1, lead_t + [m, m]) + 4 * np.eye(m)
+        t = np.tril(t) if op != "triu_solve" else np.triu(t)
+        y = rng.uniform(-1, 1, lead_y + [m, j])
+        x = getattr(ref, op)(t, y)
+        full = t @ np.swapaxes(t, -1, -2) if op == "cholesky_solve" else t
+        np.testing.assert_allclose(full @ x, np.broadcast_to(y, x.shape), rtol=1e-9, atol=1e-11)
+
+
+def test_qr_lstsq_vs_lapack(ref):
+    rng = np.random.default_rng(11)
+    a, y = rng.uniform(-1, 1, (3, 12, 5)), rng.uniform(-1, 1, (3, 12, 2))
+    q, r = ref.qr_decomp(a)
+    x = ref.qr_lstsq(q, r, y)
+    for b in range(3):
+        np.testing.assert_allclose(x[b], np.linalg.lstsq(a[b], y[b], rcond=None)[0], atol=1e-13)
