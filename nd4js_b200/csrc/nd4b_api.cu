@@ -12,8 +12,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -60,6 +63,70 @@ struct Slot {
   cudaStream_t stream = nullptr;
   void* buf[kMaxBuf] = {nullptr};
   size_t cap[kMaxBuf] = {0};
+  // pinned staging ring for pageable caller memory: [0..1] inputs, [2..4] outputs
+  void* pin[5] = {nullptr};
+  size_t pin_cap[5] = {0};
+  // outputs of the chunk in flight on this slot that still have to be copied from pin[] to the caller
+  struct Pending { double* dst; const void* src; size_t bytes; } pending[3];
+  int n_pending = 0;
+};
+
+// A handful of helper threads that split large host-to-host copies (caller memory <-> pinned ring):
+// one core moves ~10 GB/s, PCIe Gen5 wants ~55 GB/s.
+class CopyPool {
+ public:
+  explicit CopyPool(int n) {
+    for (int i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    const size_t parts = std::min<size_t>(workers_.size() + 1, std::max<size_t>(1, bytes >> 20));
+    if (parts <= 1) { memcpy(dst, src, bytes); return; }
+    const size_t step = ((bytes / parts) + 63) & ~size_t(63);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (size_t i = 1; i < parts; i++) {
+        const size_t off = i * step;
+        if (off >= bytes) break;
+        tasks_.push_back({static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(step, bytes - off)});
+        outstanding_++;
+      }
+    }
+    cv_.notify_all();
+    memcpy(dst, src, std::min(step, bytes));  // the calling thread takes the first part
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return outstanding_ == 0; });
+  }
+
+ private:
+  struct Task { char* dst; const char* src; size_t bytes; };
+  void run() {
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return stop_ || !tasks_.empty(); });
+        if (stop_ && tasks_.empty()) return;
+        t = tasks_.back();
+        tasks_.pop_back();
+      }
+      memcpy(t.dst, t.src, t.bytes);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--outstanding_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<Task> tasks_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  int outstanding_ = 0;
+  bool stop_ = false;
 };
 
 struct Device {
@@ -78,6 +145,15 @@ struct Context {
   std::mutex mu;
   std::atomic<uint64_t> calls{0}, launches{0}, h2d{0}, d2h{0}, staged{0};
   int last_sweeps = 0;
+  CopyPool* pool = nullptr;   // created on first use of pageable memory
+  double t_copy = 0, t_wait = 0, t_alloc = 0;  // seconds spent in staging copies / stream waits / (re)allocation (ND4B_TRACE)
+};
+
+struct Timer {
+  double* acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit Timer(double* a) : acc(a) {}
+  ~Timer() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 Context* g_ctx = nullptr;
@@ -91,6 +167,27 @@ int ensure(Slot& s, int i, size_t bytes) {
   const size_t want = bytes + bytes / 8 + 256;
   CU(cudaMalloc(&s.buf[i], want));
   s.cap[i] = want;
+  return 0;
+}
+
+int ensure_pinned(Slot& s, int i, size_t bytes) {
+  if (s.pin_cap[i] >= bytes) return 0;
+  if (s.pin[i]) CU(cudaFreeHost(s.pin[i]));
+  s.pin[i] = nullptr;
+  s.pin_cap[i] = 0;
+  const size_t want = bytes + bytes / 8 + 256;
+  CU(cudaHostAlloc(&s.pin[i], want, cudaHostAllocPortable));
+  s.pin_cap[i] = want;
+  return 0;
+}
+
+// Copies the finished outputs of the chunk that last ran on `slot` from the pinned ring to the caller's memory.
+int drain_slot(Context* ctx, Slot& slot) {
+  if (slot.n_pending == 0) return 0;
+  { Timer t(&ctx->t_wait); CU(cudaStreamSynchronize(slot.stream)); }
+  Timer t(&ctx->t_copy);
+  for (int i = 0; i < slot.n_pending; i++) ctx->pool->copy(slot.pending[i].dst, slot.pending[i].src, slot.pending[i].bytes);
+  slot.n_pending = 0;
   return 0;
 }
 
@@ -203,9 +300,17 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
   const size_t per_unit = std::max<size_t>(std::max(in_bytes_unit, out_bytes_unit), 8);
   const int64_t chunk_units = std::max<int64_t>(1, (int64_t)(ctx->chunk_bytes / per_unit));
   std::vector<bool> in_pinned, out_pinned;
-  for (auto& s : ins) in_pinned.push_back(is_pinned(s.in));
-  for (auto& s : outs) out_pinned.push_back(is_pinned(s.out));
+  bool any_pageable = false;
+  for (auto& s : ins) { in_pinned.push_back(is_pinned(s.in)); any_pageable |= !in_pinned.back(); }
+  for (auto& s : outs) { out_pinned.push_back(is_pinned(s.out)); any_pageable |= !out_pinned.back(); }
+  if (any_pageable && !ctx->pool) {
+    int n = (int)std::thread::hardware_concurrency() / 2 - 1;
+    if (const char* e = getenv("ND4B_COPY_THREADS")) n = atoi(e) - 1;
+    ctx->pool = new CopyPool(std::max(0, std::min(n, 7)));
+  }
 
+  for (auto& dv : ctx->devs)
+    for (auto& sl : dv.slots) sl.n_pending = 0;  // nothing may survive from a call that returned early with an error
   struct Shard { int64_t b0, b1, next; int chunk; };
   std::vector<Shard> shards(nd);
   for (int d = 0; d < nd; d++) {
@@ -225,7 +330,8 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
       CU(cudaSetDevice(dev.id));
       Slot& slot = dev.slots[sh.chunk % kSlots];
       const int64_t cnt = std::min(chunk_units, sh.b1 - sh.next);
-      // the slot's buffers are reused: stream order guarantees the previous chunk on this slot is done
+      // the slot's device buffers are reused in stream order; its pinned ring must be drained first
+      if (int rc = drain_slot(ctx, slot)) return rc;
       ChunkArgs a{};
       a.dev = &dev;
       a.stream = slot.stream;
@@ -234,9 +340,16 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
       for (size_t i = 0; i < ins.size(); i++) {
         const size_t bytes = (size_t)cnt * ins[i].elems * 8;
         if (int rc = ensure(slot, (int)i, bytes)) return rc;
-        CU(cudaMemcpyAsync(slot.buf[i], ins[i].in + sh.next * ins[i].elems, bytes, cudaMemcpyHostToDevice, slot.stream));
+        const void* src = ins[i].in + sh.next * ins[i].elems;
+        if (!in_pinned[i]) {  // pageable caller memory: stage through the slot's pinned buffer
+          { Timer t(&ctx->t_alloc); if (int rc = ensure_pinned(slot, (int)i, bytes)) return rc; }
+          { Timer t(&ctx->t_wait); CU(cudaStreamSynchronize(slot.stream)); }  // the previous H2D out of this pinned buffer has finished
+          { Timer t(&ctx->t_copy); ctx->pool->copy(slot.pin[i], src, bytes); }
+          src = slot.pin[i];
+          ctx->staged += bytes;
+        }
+        CU(cudaMemcpyAsync(slot.buf[i], src, bytes, cudaMemcpyHostToDevice, slot.stream));
         ctx->h2d += bytes;
-        if (!in_pinned[i]) ctx->staged += bytes;
         a.in[i] = static_cast<const double*>(slot.buf[i]);
       }
       for (size_t i = 0; i < outs.size(); i++) {
@@ -254,9 +367,16 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
       if (int rc = launch(a)) return rc;
       for (size_t i = 0; i < outs.size(); i++) {
         const size_t bytes = (size_t)cnt * outs[i].elems * 8;
-        CU(cudaMemcpyAsync(outs[i].out + sh.next * outs[i].elems, a.out[i], bytes, cudaMemcpyDeviceToHost, slot.stream));
+        double* dst = outs[i].out + sh.next * outs[i].elems;
+        if (!out_pinned[i]) {
+          if (int rc = ensure_pinned(slot, 2 + (int)i, bytes)) return rc;
+          CU(cudaMemcpyAsync(slot.pin[2 + i], a.out[i], bytes, cudaMemcpyDeviceToHost, slot.stream));
+          slot.pending[slot.n_pending++] = {dst, slot.pin[2 + i], bytes};
+          ctx->staged += bytes;
+        } else {
+          CU(cudaMemcpyAsync(dst, a.out[i], bytes, cudaMemcpyDeviceToHost, slot.stream));
+        }
         ctx->d2h += bytes;
-        if (!out_pinned[i]) ctx->staged += bytes;
       }
       sh.next += cnt;
       sh.chunk++;
@@ -264,8 +384,14 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
   }
   for (int d = 0; d < nd; d++) {
     CU(cudaSetDevice(ctx->devs[d].id));
-    for (auto& s : ctx->devs[d].slots) CU(cudaStreamSynchronize(s.stream));
+    for (auto& s : ctx->devs[d].slots) {
+      CU(cudaStreamSynchronize(s.stream));
+      if (int rc = drain_slot(ctx, s)) return rc;
+    }
   }
+  if (getenv("ND4B_TRACE"))
+    fprintf(stderr, "[nd4b] pipeline: staging copies %.1f ms, stream waits %.1f ms, pinned alloc %.1f ms (cumulative)\n",
+            1e3 * ctx->t_copy, 1e3 * ctx->t_wait, 1e3 * ctx->t_alloc);
   return ND4B_OK;
 }
 
@@ -340,11 +466,13 @@ int nd4b_shutdown(void) {
     for (auto& s : d.slots) {
       if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
       for (auto& b : s.buf) if (b) cudaFree(b);
+      for (auto& b : s.pin) if (b) cudaFreeHost(b);
     }
     for (auto& r : d.resident) if (r) cudaFree(r);
     if (d.d_info) cudaFree(d.d_info);
     if (d.d_ints) cudaFree(d.d_ints);
   }
+  delete g_ctx->pool;
   delete g_ctx;
   g_ctx = nullptr;
   return ND4B_OK;

@@ -56,11 +56,11 @@ def asarray(x):
     """nd_array.js:102-126: NDArrays pass through, nested sequences are copied into a new NDArray."""
     if isinstance(x, NDArray):
         return x
-    a = np.array(x)
+    a = np.asarray(x)  # numpy input is wrapped without a copy (inputs are never written); nested lists are copied
     if a.dtype.kind == "c":
         raise TypeError("complex128 is outside the float64 hot path")
-    if a.dtype.kind in "iub" :
-        a = a.astype(np.int32)
+    if a.dtype.kind in "iub":
+        a = a.astype(np.int32, copy=False)
     elif a.dtype != np.float32:
-        a = a.astype(np.float64)
+        a = a.astype(np.float64, copy=False)
     return from_numpy(a)
