@@ -128,7 +128,7 @@ def run_reference(args):
                                    "host has %d cores, reference is single-threaded" % (sample, units, os.cpu_count())},
         "e2e": {"value": val, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def _ref_case(name, n, rng, nd4ref):
@@ -273,8 +273,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; stdout carries ONE JSON line
+        # NCCL writes its banner / debug lines to stdout by default; stdout carries ONE JSON line, so send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nd.init([local])
     lib = nd.load()
@@ -304,8 +304,8 @@ def run_ours(args):
 
     if args.kernel_only:  # tuning aid: device-resident timing only, not a bench line
         if rank == 0:
-            print(json.dumps({"workload": args.workload, "ms_per_launch": 1e3 * launch_s, "matrices_per_s": value,
-                              "gflops": value * flop_unit / 1e9, "hbm_gbs_algorithmic": achieved_gbs, "sweeps": sweeps}))
+            emit({"workload": args.workload, "ms_per_launch": 1e3 * launch_s, "matrices_per_s": value,
+                  "gflops": value * flop_unit / 1e9, "hbm_gbs_algorithmic": achieved_gbs, "sweeps": sweeps})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -402,12 +402,30 @@ def run_ours(args):
                                           "(no JS engine in this image); host has %d cores, the reference is single-threaded"
                                           % (sample, reps, dt, os.cpu_count())}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints was diverted to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    # NCCL / torch print banners (e.g. "NCCL version ...") on fd 1: keep the contract's stdout clean
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
