@@ -806,6 +806,7 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
       cudaError_t e = cudaFuncSetAttribute(svd64_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64Smem);
       if (e != cudaSuccess) return e;
@@ -814,11 +815,12 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     static int variant = -1;
     if (variant < 0) {
       const char* ev = getenv("ND4B_SVD_VARIANT");
-      variant = ev ? atoi(ev) : 0;
+      variant = ev ? atoi(ev) : 4;
     }
     if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail);
     else if (variant == 3) svd64d_kernel<<<(unsigned)batch, 256, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     else if (variant == 2) svd64_kernel<2, 3><<<(unsigned)batch, 128, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    else if (variant == 4) svd64_kernel<2, 2><<<(unsigned)batch, 128, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     else svd64_kernel<4, 2><<<(unsigned)batch, 256, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     return cudaGetLastError();
   }

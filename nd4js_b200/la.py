@@ -8,6 +8,7 @@ Same names, argument meaning, result shapes and error texts as the reference:
   tril_solve(L,Y), triu_solve(U,Y)     src/la/tri.js:156-293
   cholesky_solve(L,y)                  src/la/cholesky.js:75-144
   qr_lstsq(Q,R,y) / qr_lstsq((Q,R),y)  src/la/qr.js:186-273
+  svd_rank(sv), svd_lstsq(U,sv,V,y), svd_solve(U,sv,V,y)   src/la/svd.js:31-226 (rank cut sqrt(eps)*sv[0])
 Argument handling (asarray, upcasts, shape checks) stays on the host as it stays in JS in the
 reference; all arithmetic happens in libnd4b.so on the GPU.  Float64 only: other result dtypes raise
 (the reference's int32/float32/complex paths are outside the hot path and there is no CPU fallback).
@@ -241,3 +242,71 @@ def qr_lstsq(Q, R, y=None):
     x = np.zeros(x_top.shape[:-2] + (i_, j_))
     x[..., :l, :] = x_top
     return NDArray(np.asarray(x.shape, np.int32), x.reshape(-1))
+
+
+_SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))
+
+
+def svd_rank(sv):
+    """Numerical rank per matrix: number of leading singular values > sqrt(eps)*sv[0] (svd.js:31-58)."""
+    sv = asarray(sv)
+    d = sv.numpy().astype(np.float64, copy=False)
+    if not np.isfinite(d).all():
+        raise ValueError("svd_rank(): NaN or Infinity encountered.")
+    t = _SQRT_EPS * np.abs(d[..., :1])
+    below = np.abs(d) <= t
+    r = np.where(below.any(axis=-1), below.argmax(axis=-1), d.shape[-1]).astype(np.int32)
+    shape = np.asarray(d.shape[:-1] if d.ndim > 1 else (1,), np.int32)
+    return NDArray(shape, np.ascontiguousarray(r).reshape(-1))
+
+
+def svd_lstsq(U, sv=None, V=None, y=None):
+    """x = V^T diag(1/sv[:rank]) U^T y (svd.js:103-226): two GPU matmuls around a host-side scaling of the
+    [M,J] intermediate; the rank cut is the reference's."""
+    if y is None:
+        if V is not None:
+            raise ValueError("svd_lstsq(Q,R,P, y): Either 2 ([Q,R,P], y) or 4 arguments (Q,R,P, y) expected.")
+        y = sv
+        U, sv, V = U
+    U, sv, V, y = asarray(U), asarray(sv), asarray(V), asarray(y)
+    if U.ndim < 2:
+        raise ValueError("svd_lstsq(U,sv,V, y): U.ndim must be at least 2.")
+    if sv.ndim < 1:
+        raise ValueError("svd_lstsq(U,sv,V, y): sv.ndim must be at least 1.")
+    if V.ndim < 2:
+        raise ValueError("svd_lstsq(U,sv,V, y): V.ndim must be at least 2.")
+    if y.ndim < 2:
+        raise ValueError("svd_lstsq(U,sv,V, y): y.ndim must be at least 2.")
+    n, m = int(U.shape[-2]), int(U.shape[-1])
+    if n != int(y.shape[-2]):
+        raise ValueError("svd_lstsq(U,sv,V, y): U and y don't match.")
+    if m != int(sv.shape[-1]):
+        raise ValueError("svd_lstsq(U,sv,V, y): U and sv don't match.")
+    if m != int(V.shape[-2]):
+        raise ValueError("svd_lstsq(U,sv,V, y): V and sv don't match.")
+    s = sv.numpy().astype(np.float64, copy=False)
+    try:
+        np.broadcast_shapes(tuple(U.shape[:-2]), tuple(V.shape[:-2]), tuple(y.shape[:-2]), s.shape[:-1])
+    except ValueError:
+        raise ValueError("svd_lstsq(U,sv,V, y): U,sv,V,y not broadcast-compatible.")
+    if not np.isfinite(s).all():
+        raise ValueError("svd_solve(): NaN or Infinity encountered.")
+    rank = svd_rank(sv).numpy().reshape(s.shape[:-1]) if s.ndim > 1 else svd_rank(sv).numpy().reshape(())
+    keep = np.arange(m) < np.asarray(rank)[..., None]
+    inv = np.where(keep, 1.0 / np.where(keep, s, 1.0), 0.0)
+    tmp = matmul2(U.T, y).numpy() * inv[..., :, None]          # diag(1/sv) U^T y, zero beyond the rank
+    return matmul2(V.T, np.ascontiguousarray(tmp))
+
+
+def svd_solve(U, sv=None, V=None, y=None):
+    """svd_lstsq for square systems; raises when a matrix is numerically singular (svd.js:61-100)."""
+    if y is None:
+        y = sv
+        U, sv, V = U
+    U, sv, V = asarray(U), asarray(sv), asarray(V)
+    if int(U.shape[-2]) != int(V.shape[-1]):
+        raise ValueError("rrqr_solve(Q,R,P, y): System not square.")
+    x = svd_lstsq(U, sv, V, y)
+    if (svd_rank(sv).numpy() < int(sv.shape[-1])).any():
+        raise np.linalg.LinAlgError("svd_solve(): singular matrix (SingularMatrixSolveError in the reference)")
+    return x

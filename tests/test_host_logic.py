@@ -108,3 +108,11 @@ def test_two_rank_gloo_sharding_reassembles_the_reference_result(ref, tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_svd_rank_host_logic():
+    from nd4js_b200 import la
+    sv = np.array([[3.0, 1.0, 1e-9, 0.0], [2.0, 1.0, 0.5, 0.25], [0.0, 0.0, 0.0, 0.0]])
+    assert list(la.svd_rank(sv).numpy()) == [2, 4, 0]   # cut at sqrt(eps)*sv[0], svd.js:31-58
+    with pytest.raises(ValueError, match="NaN or Infinity"):
+        la.svd_rank(np.array([1.0, np.nan]))
