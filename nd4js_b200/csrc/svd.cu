@@ -40,6 +40,19 @@ __device__ __forceinline__ Rot make_rotation(double a, double b, double d) {
   return r;
 }
 
+// Reciprocal square root for normal-range arguments without the library's special-case branches: hardware seed
+// (MUFU.RSQ64H, ~2^-22) and two third-order Newton steps (full double precision up to ~1 ulp).
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double e = fma(-x * y, y, 1.0);   // 1 - x y^2
+    y = fma(y * e, fma(0.375, e, 0.5), y);  // y (1 + e/2 + 3 e^2 / 8)
+  }
+  return y;
+}
+
 // Tournament pairing of n2 (even) players, step s in [0,n2-1), slot P in [0,n2/2).
 __device__ __forceinline__ void rr_pair(int n2, int s, int P, int& p, int& q) {
   const int m1 = n2 - 1;
@@ -651,6 +664,267 @@ svd64d_kernel(const double* __restrict__ A, double* __restrict__ U, double* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// 64x64, register-resident, column-block per warp ("CB").
+//
+// The kernels above split the ROWS of a column over several warps, so every step needs a cross-warp reduction
+// (smem + CTA barrier) and a single parameter warp that all others wait for.  Here a warp owns 16 whole columns
+// (slots): lane l holds rows l and l+32 of G and of V for those 16 slots.  The 8 dot products of a step are
+// reduced inside the warp (recursive halving over lane bits 4,3,2, then a 2-stage butterfly), the 4-lane group g
+// computes the rotation of pair g, and the 8 (c, s) are gathered with shuffles: no shared memory, no barrier and no
+// central parameter computation inside a step.  The odd-even pairing shifts by one slot between A and B steps, so the
+// ownership boundary migrates instead: before a B step each warp hands its first column to its left neighbour, after
+// it the (rotated) column comes back — one 4-double-per-lane exchange through shared memory and one barrier per step.
+// ------------------------------------------------------------------------------------------------
+//
+// Scaled ("fast", square-root-free) rotations: column p is stored as g_p = D_p * gh_p with one scalar D_p per
+// column.  The plane rotation  g_p' = c g_p - s g_q,  g_q' = s g_p + c g_q  then becomes
+//     gh_p' = gh_p - alpha gh_q,   gh_q' = gh_q + beta gh_p,   D_p' = c D_p,  D_q' = c D_q,
+//     alpha = t D_q / D_p,  beta = t D_p / D_q,  t = s / c,
+// i.e. TWO independent FMAs per element pair instead of two multiplications and two FMAs; V shares the D of G
+// because it undergoes the same rotations from D = 1.  |t| <= 1, so c >= 1/sqrt 2: within one sweep (63 rotations per
+// column) D stays above 3e-10 and |gh| grows by at most 2^31.5; D is folded back into the columns after every sweep.
+// D and 1/D are both tracked (1/c is a by-product of the rotation set-up), so no division is needed.
+struct CbState {
+  double g0[16], g1[16], v0[16], v1[16];  // rows l and l+32 of G-hat and V-hat for the warp's 16 slots
+  double xg0, xg1, xv0, xv1;              // the borrowed boundary column (right neighbour's first slot) in B steps
+  double e, o;                            // cached TRUE |g|^2 of slots 2*grp and 2*grp+1 (replicated in the 4-lane group)
+  double de, dei, dq, dqi;                // scale D and 1/D of the even slot (de, dei) and of the odd slot (dq, dqi)
+  double xn, xd, xdi;                     // norm and scale of the borrowed column
+};
+
+struct CbRot { double alpha, beta; };
+
+// One lane per pair: threshold test and rotation set-up from the true norms and the true dot product.
+// Outputs the scaled-rotation multipliers, and the norms/scales of the two columns AFTER the rotation (before exchange).
+__device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, double Dp, double Dpi, double Dq, double Dqi,
+                                           bool have, double tol2, double& na2, double& nb2, double& Dp2, double& Dpi2,
+                                           double& Dq2, double& Dqi2, int& rotated) {
+  CbRot r;
+  r.alpha = 0.0; r.beta = 0.0;
+  na2 = na; nb2 = nb; Dp2 = Dp; Dpi2 = Dpi; Dq2 = Dq; Dqi2 = Dqi;
+  const double d = dhat * Dp * Dq;
+  if (have && d * d > tol2 * na * nb) {
+    double num = nb - na, den = 2.0 * d;
+    if (fabs(num) + fabs(den) < 1e-140) { num *= 0x1p600; den *= 0x1p600; }  // only the ratio matters; keep num^2+den^2 normal
+    const double rh = rsqrt_nr(fma(num, num, den * den));
+    const double c2 = fabs(num) * rh, s2 = fabs(den) * rh;   // cos 2theta, |sin 2theta|
+    const double hc = fma(0.5, c2, 0.5);                     // c^2
+    const double rc = rsqrt_nr(hc);                          // 1/c
+    const double c = hc * rc;
+    double sn = 0.5 * s2 * rc;                               // |s|
+    if ((num < 0.0) != (den < 0.0)) sn = -sn;
+    const double t = sn * rc;
+    r.alpha = t * Dq * Dpi;
+    r.beta = t * Dp * Dqi;
+    Dp2 = c * Dp; Dq2 = c * Dq; Dpi2 = rc * Dpi; Dqi2 = rc * Dqi;
+    const double cc = hc, ss = sn * sn, csd = 2.0 * c * sn * d;
+    na2 = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);         // |c p - s q|^2
+    nb2 = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);          // |s p + c q|^2
+    rotated = 1;
+  }
+  return r;
+}
+
+// reduce 8 per-lane partials so that every lane of 4-lane group grp holds the warp total of element grp
+__device__ __forceinline__ double cb_reduce8(double (&pd)[8], int lane) {
+  halve<8>(pd, (lane & 16) != 0, 16);
+  double h4[4] = {pd[0], pd[1], pd[2], pd[3]};
+  halve<4>(h4, (lane & 8) != 0, 8);
+  double h2[2] = {h4[0], h4[1]};
+  halve<2>(h2, (lane & 4) != 0, 4);
+  double d = h2[0];
+  d += shfl_xor(d, 2);
+  d += shfl_xor(d, 1);
+  return d;
+}
+
+// (p, q) -> (p - alpha q, q + beta p), stored exchanged: first slot <- new q, second slot <- new p
+__device__ __forceinline__ void fast_rot_swap(double& xa, double& xb, double alpha, double beta) {
+  const double np = fma(-alpha, xb, xa);
+  const double nq = fma(beta, xa, xb);
+  xa = nq;
+  xb = np;
+}
+
+template <bool STEP_B>
+__device__ __forceinline__ void cb_step(CbState& st, double2* wcs, int warp, int lane, double tol2, int& rotated) {
+  const int grp = lane >> 2;
+  // slot pairs of this step in register terms: A: (2j, 2j+1); B: (2j+1, 2j+2) with slot 16 = the borrowed column
+  double pd[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (!STEP_B) pd[j] = fma(st.g1[2 * j], st.g1[2 * j + 1], st.g0[2 * j] * st.g0[2 * j + 1]);
+    else if (j < 7) pd[j] = fma(st.g1[2 * j + 1], st.g1[2 * j + 2], st.g0[2 * j + 1] * st.g0[2 * j + 2]);
+    else pd[j] = fma(st.g1[15], st.xg1, st.g0[15] * st.xg0);
+  }
+  const double dhat = cb_reduce8(pd, lane);
+  double na, nb, Dp, Dpi, Dq, Dqi;
+  bool have = true;
+  if (!STEP_B) { na = st.e; nb = st.o; Dp = st.de; Dpi = st.dei; Dq = st.dq; Dqi = st.dqi; }
+  else {
+    const double e_next = __shfl_down_sync(kFull, st.e, 4);      // even slot of the next group
+    const double de_next = __shfl_down_sync(kFull, st.de, 4);
+    const double dei_next = __shfl_down_sync(kFull, st.dei, 4);
+    na = st.o; Dp = st.dq; Dpi = st.dqi;
+    nb = (grp < 7) ? e_next : st.xn;
+    Dq = (grp < 7) ? de_next : st.xd;
+    Dqi = (grp < 7) ? dei_next : st.xdi;
+    have = (grp < 7) || (warp < 3);                                // slot 64 does not exist
+  }
+  double na2, nb2, Dp2, Dpi2, Dq2, Dqi2;
+  const CbRot r = cb_params(dhat, na, nb, Dp, Dpi, Dq, Dqi, have, tol2, na2, nb2, Dp2, Dpi2, Dq2, Dqi2, rotated);
+  // exchanged storage: first slot of the pair <- rotated q, second slot <- rotated p
+  if (!STEP_B) {
+    st.e = nb2; st.de = Dq2; st.dei = Dqi2;
+    st.o = na2; st.dq = Dp2; st.dqi = Dpi2;
+  } else {
+    const double n_prev = __shfl_up_sync(kFull, na2, 4);          // group grp-1's second slot is my even slot
+    const double d_prev = __shfl_up_sync(kFull, Dp2, 4);
+    const double di_prev = __shfl_up_sync(kFull, Dpi2, 4);
+    if (have) { st.o = nb2; st.dq = Dq2; st.dqi = Dqi2; }
+    if (grp > 0) { st.e = n_prev; st.de = d_prev; st.dei = di_prev; }
+    if (grp == 7 && have) { st.xn = na2; st.xd = Dp2; st.xdi = Dpi2; }
+  }
+  // (alpha, beta) of the 8 pairs to every lane: group leaders publish to a warp-private smem line, uniform 16-byte reads
+  __syncwarp();
+  if ((lane & 3) == 0) wcs[grp] = make_double2(r.alpha, r.beta);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const double2 ab = wcs[j];
+    if (!STEP_B) {
+      fast_rot_swap(st.g0[2 * j], st.g0[2 * j + 1], ab.x, ab.y); fast_rot_swap(st.g1[2 * j], st.g1[2 * j + 1], ab.x, ab.y);
+      fast_rot_swap(st.v0[2 * j], st.v0[2 * j + 1], ab.x, ab.y); fast_rot_swap(st.v1[2 * j], st.v1[2 * j + 1], ab.x, ab.y);
+    } else if (j < 7) {
+      fast_rot_swap(st.g0[2 * j + 1], st.g0[2 * j + 2], ab.x, ab.y); fast_rot_swap(st.g1[2 * j + 1], st.g1[2 * j + 2], ab.x, ab.y);
+      fast_rot_swap(st.v0[2 * j + 1], st.v0[2 * j + 2], ab.x, ab.y); fast_rot_swap(st.v1[2 * j + 1], st.v1[2 * j + 2], ab.x, ab.y);
+    } else if (warp < 3) {  // the last warp has no right neighbour: slot 63 stays where it is
+      fast_rot_swap(st.g0[15], st.xg0, ab.x, ab.y); fast_rot_swap(st.g1[15], st.xg1, ab.x, ab.y);
+      fast_rot_swap(st.v0[15], st.xv0, ab.x, ab.y); fast_rot_swap(st.v1[15], st.xv1, ab.x, ab.y);
+    }
+  }
+}
+
+constexpr size_t kSvd64CbSmem = sizeof(double) * (2 * 64 * kSvd64LD + 64 + 2 * 4 * 136 + 4 * 16) + sizeof(int) * (64 * 3 + 4);
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
+               int64_t batch, int* sweeps_out, int* fail_out) {
+  constexpr int N = 64, LD = kSvd64LD, XS = 136;       // XS: doubles per exchange record (4*32 column values + norm, D, 1/D)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Gs = reinterpret_cast<double*>(smem_raw);
+  double* Vs = Gs + N * LD;
+  double* sq = Vs + N * LD;
+  double* xch = sq + N;                                 // [2 directions][4 warps][XS]
+  double2* wcs_all = reinterpret_cast<double2*>(xch + 2 * 4 * XS);   // [4 warps][8] (alpha, beta) of the current step
+  int* perm = reinterpret_cast<int*>(wcs_all + 4 * 8);
+  int* zero_flag = perm + N;
+  int* done_flag = zero_flag + N;
+
+  const int64_t m = blockIdx.x;
+  if (m >= batch) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2;
+  const double* a_in = A + m * (N * N);
+  double2* wcs = wcs_all + 8 * warp;
+  double* wsc = reinterpret_cast<double*>(wcs);         // the same 16 doubles, reused for the per-slot scales between sweeps
+
+  CbState st;
+#pragma unroll
+  for (int s = 0; s < 16; s += 2) {
+    const double2 t0 = ldg2_stream(a_in + lane * N + 16 * warp + s);
+    const double2 t1 = ldg2_stream(a_in + (lane + 32) * N + 16 * warp + s);
+    st.g0[s] = t0.x; st.g0[s + 1] = t0.y;
+    st.g1[s] = t1.x; st.g1[s + 1] = t1.y;
+  }
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    st.v0[s] = (16 * warp + s == lane) ? 1.0 : 0.0;
+    st.v1[s] = (16 * warp + s == lane + 32) ? 1.0 : 0.0;
+  }
+  st.xg0 = st.xg1 = st.xv0 = st.xv1 = st.xn = 0.0;
+  st.xd = st.xdi = 1.0;
+
+  const double tol2 = (N * kEps) * (N * kEps);
+  int sweeps = 0;
+  bool converged = false;
+  while (sweeps < kMaxSweeps && !converged) {
+    sweeps++;
+    int rotated = 0;
+    st.de = st.dei = st.dq = st.dqi = 1.0;
+    {  // exact slot norms: 16 values -> 2 per 4-lane group
+      double n2[16];
+#pragma unroll
+      for (int s = 0; s < 16; s++) n2[s] = fma(st.g1[s], st.g1[s], st.g0[s] * st.g0[s]);
+      halve<16>(n2, (lane & 16) != 0, 16);
+      double h8[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) h8[k] = n2[k];
+      halve<8>(h8, (lane & 8) != 0, 8);
+      double h4[4] = {h8[0], h8[1], h8[2], h8[3]};
+      halve<4>(h4, (lane & 4) != 0, 4);
+      double e = h4[0], o = h4[1];
+      e += shfl_xor(e, 2); o += shfl_xor(o, 2);
+      e += shfl_xor(e, 1); o += shfl_xor(o, 1);
+      st.e = e; st.o = o;
+    }
+#pragma unroll 1
+    for (int sp2 = 0; sp2 < N / 2; sp2++) {
+      cb_step<false>(st, wcs, warp, lane, tol2, rotated);
+      // hand my first column (slot 16w) to the left neighbour for the B step
+      double* out = xch + warp * XS;
+      if (warp > 0) {
+        out[lane] = st.g0[0]; out[32 + lane] = st.g1[0]; out[64 + lane] = st.v0[0]; out[96 + lane] = st.v1[0];
+        if (lane == 0) { out[128] = st.e; out[129] = st.de; out[130] = st.dei; }   // group 0's even slot
+      }
+      __syncthreads();
+      if (warp < 3) {
+        const double* in = xch + (warp + 1) * XS;
+        st.xg0 = in[lane]; st.xg1 = in[32 + lane]; st.xv0 = in[64 + lane]; st.xv1 = in[96 + lane];
+        st.xn = in[128]; st.xd = in[129]; st.xdi = in[130];
+      }
+      cb_step<true>(st, wcs, warp, lane, tol2, rotated);
+      // give the borrowed (rotated) column back
+      double* out2 = xch + 4 * XS + (warp + 1) * XS;
+      if (warp < 3) {
+        out2[lane] = st.xg0; out2[32 + lane] = st.xg1; out2[64 + lane] = st.xv0; out2[96 + lane] = st.xv1;
+        if (lane == 28) { out2[128] = st.xn; out2[129] = st.xd; out2[130] = st.xdi; }   // a lane of group 7
+      }
+      __syncthreads();
+      if (warp > 0) {
+        const double* in2 = xch + 4 * XS + warp * XS;
+        st.g0[0] = in2[lane]; st.g1[0] = in2[32 + lane]; st.v0[0] = in2[64 + lane]; st.v1[0] = in2[96 + lane];
+        if (grp == 0) { st.e = in2[128]; st.de = in2[129]; st.dei = in2[130]; }
+      }
+    }
+    // fold the scales back into the columns: every lane needs D of all 16 slots of its warp
+    __syncwarp();
+    if ((lane & 3) == 0) { wsc[2 * grp] = st.de; wsc[2 * grp + 1] = st.dq; }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const double D = wsc[s];
+      st.g0[s] *= D; st.g1[s] *= D; st.v0[s] *= D; st.v1[s] *= D;
+    }
+    __syncwarp();
+    converged = !__syncthreads_or(rotated);
+  }
+  if (tid == 0) {
+    if (sweeps_out) atomicMax(sweeps_out, sweeps);
+    if (!converged && fail_out) atomicExch(fail_out, 1);
+  }
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    Gs[(16 * warp + s) * LD + lane] = st.g0[s];
+    Gs[(16 * warp + s) * LD + lane + 32] = st.g1[s];
+    Vs[(16 * warp + s) * LD + lane] = st.v0[s];
+    Vs[(16 * warp + s) * LD + lane + 32] = st.v1[s];
+  }
+  __syncthreads();
+  svd64_epilogue<128>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic shape.  mm = max(rows,cols) (vector length), n = min(rows,cols) (number of columns of G).
 // scratch per matrix: Gt[n*mm], Vt[n*n], sig[n], then ints perm[n], zero[n], done[n] (packed in doubles)
 // ------------------------------------------------------------------------------------------------
@@ -805,6 +1079,8 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
       cudaError_t e = cudaFuncSetAttribute(svd64_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64cb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64CbSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64cb_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64CbSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
@@ -815,9 +1091,11 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     static int variant = -1;
     if (variant < 0) {
       const char* ev = getenv("ND4B_SVD_VARIANT");
-      variant = ev ? atoi(ev) : 4;
+      variant = ev ? atoi(ev) : 5;
     }
     if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    else if (variant == 5) svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    else if (variant == 6) svd64cb_kernel<3><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     else if (variant == 3) svd64d_kernel<<<(unsigned)batch, 256, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     else if (variant == 2) svd64_kernel<2, 3><<<(unsigned)batch, 128, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     else if (variant == 4) svd64_kernel<2, 2><<<(unsigned)batch, 128, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
