@@ -350,7 +350,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "kernel": {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
-                                    "c4": "qr64x32_kernel", "c5": "svd64_kernel"}[args.workload],
+                                    "c4": "qr64x32_kernel", "c5": "svd64cb_kernel"}[args.workload],
                          "algorithmic_bytes_per_unit": bpu, "units_per_launch": units},
             "clocks": clocks,
         }

@@ -426,12 +426,10 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
     if (I >= 96 && J >= 96 && t128 >= sm_count) return launch_pipe<2, 4, 8, 4, 3>(s, A, B, C, batch, I, K, J, map);
     if (I >= 48 && J >= 48 && t64 >= 2LL * sm_count) return launch_pipe<2, 2, 4, 4, 4>(s, A, B, C, batch, I, K, J, map);
     if (I >= 48 && J >= 24) {
-      // few tiles (e.g. one 512^3 -> 128 CTAs): 8 warps of 16x16 per 64x32 tile keep two warps on every SM sub-partition
-      static int v = -1;
-      if (v < 0) { const char* e = getenv("ND4B_GEMM_SMALL"); v = e ? atoi(e) : 2; }
+      // few tiles (e.g. one 512^3): 32x32 tiles with 4 warps of 16x16 put >= 2 CTAs on most SMs
+      // measured on one 512^3: 64x32 tiles/4 warps 18.7 us, 64x32/8 warps 17.6 us, 32x32/4 warps (256 CTAs) 16.4 us
       const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
-      if (v == 1 && t6432 < 2LL * sm_count) return launch_pipe<4, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
-      if (v == 2 && t6432 < 2LL * sm_count) return launch_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
+      if (t6432 < 2LL * sm_count) return launch_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
       return launch_pipe<4, 1, 2, 4, 4>(s, A, B, C, batch, I, K, J, map);
     }
   }

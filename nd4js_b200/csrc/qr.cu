@@ -331,13 +331,10 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
   const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q) |
                          reinterpret_cast<uintptr_t>(R)) & 15) == 0;
   if (rows == 64 && cols == 32 && aligned) {
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("ND4B_QR_VARIANT"); variant = e ? atoi(e) : 0; }
+    // 222 registers -> 2 CTAs of 4 warps per SM.  Capping registers for 3 CTAs (168) or using 1-/2-warp CTAs was
+    // measured slower (spills): 2.05 / 2.27 / 2.20 ms vs 1.86 ms on C4.
     if (batch > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if (variant == 1) qr64x32_kernel<1, 9><<<(unsigned)batch, 32, 0, s>>>(A, Q, R, batch);
-    else if (variant == 2) qr64x32_kernel<4, 3><<<(unsigned)((batch + 3) / 4), 128, 0, s>>>(A, Q, R, batch);
-    else if (variant == 3) qr64x32_kernel<2, 5><<<(unsigned)((batch + 1) / 2), 64, 0, s>>>(A, Q, R, batch);
-    else qr64x32_kernel<kQrWarps, 2><<<(unsigned)((batch + kQrWarps - 1) / kQrWarps), kQrWarps * 32, 0, s>>>(A, Q, R, batch);
+    qr64x32_kernel<kQrWarps, 2><<<(unsigned)((batch + kQrWarps - 1) / kQrWarps), kQrWarps * 32, 0, s>>>(A, Q, R, batch);
     return cudaGetLastError();
   }
   const int L = rows < cols ? rows : cols;

@@ -11,8 +11,11 @@
 // pairs are visited in a round-robin (tournament) order: n/2 disjoint pairs per step, n-1 steps per sweep;
 // the same rotations accumulate V.  Then sv_j = |g_j|, U = G diag(1/sv).
 //
-//  * svd64_kernel      : 64x64; one CTA (256 threads) per matrix; G and V column-major in shared memory;
-//                        8 lanes per column pair, 32 pairs (one full tournament step) in flight per CTA.
+//  * svd64cb_kernel    : 64x64, production: one CTA (4 warps) per matrix, G and V in registers (a warp owns 16 whole
+//                        columns), odd-even ordering with exchange, square-root-free scaled rotations (2 FMAs per
+//                        element pair), dot products reduced inside the warp; see the section header below.
+//  * svd64_smem_kernel : 64x64, first version kept as the A/B baseline (ND4B_SVD_VARIANT=1): G and V column-major in
+//                        shared memory, 8 lanes per column pair, round-robin ordering.
 //  * svd_generic_kernel: any shape; one CTA per matrix, G^T and V^T in global (L2-resident) scratch.
 #include "common.cuh"
 #include "kernels.h"
@@ -273,28 +276,6 @@ svd64_smem_kernel(const double* __restrict__ A, double* __restrict__ U, double* 
   svd64_epilogue<kSvd64Threads>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
 }
 
-// ------------------------------------------------------------------------------------------------
-// 64x64, register-resident: the production kernel.
-//
-// The shared-memory kernel above moves 4 KiB through shared memory per rotated pair and is bound by that
-// bandwidth (ncu: l1tex 88 %, fp64 pipe 44 %).  Here every rotation is local to a thread:
-//   * thread (row, q) of 256 holds a quarter (16 column slots) of row `row` of G and of row `row` of V in
-//     registers; a column-pair rotation touches two registers per row, no data moves;
-//   * pairs are visited in the odd-even (Brent-Luk) order with exchange: step A rotates slots (2i,2i+1), step B
-//     slots (2i+1,2i+2), and the two rotated columns are written back swapped.  64 steps are one sweep
-//     (every pair of columns meets exactly once, 2016 pairs), and the slot pattern has period 2, so all
-//     register indices are static without unrolling the sweep;
-//   * the only cross-thread quantities are the 32 (31) dot products g_p.g_q of a step: 8 products per thread,
-//     recursive halving over the 8 row-lanes of a warp (7 shuffles), 8 warp partials combined through smem;
-//   * column norms are cached per slot (a' = a - t d, b' = b + t d, Rutishauser) and recomputed exactly at the
-//     start of every sweep; one lane per pair computes (c, s), so rotation set-up is not replicated;
-//   * (c, s) of a step are broadcast through shared memory (uniform 16-byte loads);
-//   * lanes are quarter-major (q = lane>>3) so that a quarter warp reads one (c, s) word per load.
-// ------------------------------------------------------------------------------------------------
-constexpr int kSvdR_DPART = 8 * 64;  // warp partials: 8 warps x (32 pair products | 64 slot norms)
-constexpr size_t kSvd64RegSmem = sizeof(double) * (2 * 64 * kSvd64LD + 64 /*sq*/ + kSvdR_DPART + 2 * 64 /*cs*/ + 64 /*nslot*/) +
-                                 sizeof(int) * (64 * 3 + 4);
-
 // v[0..N/2) <- v[keep half] + partner's contribution; lanes with `bit` set keep the upper half
 template <int N>
 __device__ __forceinline__ void halve(double (&v)[N], bool bit, int mask) {
@@ -306,368 +287,13 @@ __device__ __forceinline__ void halve(double (&v)[N], bool bit, int mask) {
   }
 }
 
-__device__ __forceinline__ void rot_swap(double& xa, double& xb, double c, double s) {
-  // (p, q) -> (c p - s q, s p + c q), stored exchanged: first slot <- new q, second slot <- new p
-  const double np = fma(c, xa, -(s * xb));
-  const double nq = fma(s, xa, c * xb);
-  xa = nq;
-  xb = np;
-}
-
-// Recursive halving over the RL row-lanes of a warp: x[0..N) per lane -> x[0..N/RL) per lane, where lane rl ends
-// with the sums of elements rl*(N/RL) ... ; `mask` is the highest row-lane bit.
-template <int N, int STOP>
-__device__ __forceinline__ void halve_down(double (&x)[N], int rl, int mask) {
-  if constexpr (N > STOP) {
-    halve<N>(x, (rl & mask) != 0, mask);
-    double y[N / 2];
-#pragma unroll
-    for (int k = 0; k < N / 2; k++) y[k] = x[k];
-    halve_down<N / 2, STOP>(y, rl, mask >> 1);
-#pragma unroll
-    for (int k = 0; k < STOP; k++) x[k] = y[k];
-  }
-}
-
-// One odd-even step.  NQ = threads per matrix row (4: quarter rows, 256 threads; 2: half rows, 128 threads);
-// SL = 64/NQ slots per thread, RL = 32/NQ row-lanes per warp (lane = q*RL + rl), 2*NQ warps per matrix.
-// cs holds (c, s) of pair i = (SL/2)*q + j at index NQ*j + q, so that the NQ groups of a warp read adjacent words.
-template <int NQ, bool STEP_B>
-__device__ __forceinline__ void svd64_step(double (&g)[64 / NQ], double (&v)[64 / NQ], double* dpart, double2* cs_now, double* nslot,
-                                           int* flags, int warp, int lane, int rl, int q, int pw, double tol2) {
-  constexpr int N = 64, SL = 64 / NQ, NP = SL / 2, RL = 32 / NQ, NW = 2 * NQ;
-  // ---- P1: the dot products of this step's pairs ----
-  double gR0 = 0.0, gL = 0.0, vR0 = 0.0, vL = 0.0;
-  double pd[NP];
-  if (!STEP_B) {
-#pragma unroll
-    for (int j = 0; j < NP; j++) pd[j] = g[2 * j] * g[2 * j + 1];
-  } else {
-    gR0 = __shfl_down_sync(kFull, g[0], RL);       // lane + RL = (rl, q + 1)
-    gL = __shfl_up_sync(kFull, g[SL - 1], RL);     // lane - RL = (rl, q - 1)
-    vR0 = __shfl_down_sync(kFull, v[0], RL);
-    vL = __shfl_up_sync(kFull, v[SL - 1], RL);
-#pragma unroll
-    for (int j = 0; j < NP - 1; j++) pd[j] = g[2 * j + 1] * g[2 * j + 2];
-    pd[NP - 1] = (q < NQ - 1) ? g[SL - 1] * gR0 : 0.0;
-  }
-  halve_down<NP, 1>(pd, rl, RL / 2);
-  dpart[warp * 64 + NP * q + rl] = pd[0];  // pair NP*q + rl, rows of this warp
-  __syncthreads();  // B1
-
-  // ---- P2: one lane per pair: threshold test, (c, s), cached-norm update ----
-  if (warp == pw) {
-    const int i = lane;
-    double d = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) d += dpart[w * 64 + i];
-    const int sp = STEP_B ? 2 * i + 1 : 2 * i, sqq = sp + 1;
-    const bool have = sqq < N;
-    const double na = nslot[sp], nb = have ? nslot[sqq] : 0.0;
-    double c = 1.0, s = 0.0;
-    if (have && d * d > tol2 * na * nb) {
-      // theta from cos 2theta = |num|/h, sin 2theta = |den|/h (two rsqrt, no division):
-      //   c = sqrt((1 + c2)/2),  s = sign * s2 / (2c);  norms by the exact quadratic forms
-      const double num = nb - na, den = 2.0 * d;
-      const double rh = rsqrt(fma(num, num, den * den));
-      const double c2 = fabs(num) * rh, s2 = fabs(den) * rh;
-      const double hc = fma(0.5, c2, 0.5);
-      const double rc = rsqrt(hc);
-      c = hc * rc;
-      s = 0.5 * s2 * rc;
-      if ((num < 0.0) != (den < 0.0)) s = -s;
-      const double cc = c * c, ss = s * s, csd = 2.0 * c * s * d;
-      nslot[sp] = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);   // exchanged: first slot now holds the rotated q column
-      nslot[sqq] = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);
-      flags[0] = 1;
-    } else if (have) {
-      nslot[sp] = nb;
-      nslot[sqq] = na;
-    }
-    cs_now[NQ * (i % NP) + (i / NP)] = make_double2(c, s);
-  }
-  __syncthreads();  // B2
-
-  // ---- rotate G and V with the same coefficients ----
-  if (!STEP_B) {
-#pragma unroll
-    for (int j = 0; j < NP; j++) {
-      const double2 r = cs_now[NQ * j + q];
-      rot_swap(g[2 * j], g[2 * j + 1], r.x, r.y);
-      rot_swap(v[2 * j], v[2 * j + 1], r.x, r.y);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < NP - 1; j++) {
-      const double2 r = cs_now[NQ * j + q];
-      rot_swap(g[2 * j + 1], g[2 * j + 2], r.x, r.y);
-      rot_swap(v[2 * j + 1], v[2 * j + 2], r.x, r.y);
-    }
-    if (q < NQ - 1) {  // pair NP*q + NP-1 = (my last slot, right neighbour's slot 0): first slot <- s p + c q
-      const double2 r = cs_now[NQ * (NP - 1) + q];
-      g[SL - 1] = fma(r.y, g[SL - 1], r.x * gR0);
-      v[SL - 1] = fma(r.y, v[SL - 1], r.x * vR0);
-    }
-    if (q > 0) {  // pair NP*q - 1 = (left neighbour's last slot, my slot 0): second slot <- c p - s q
-      const double2 r = cs_now[NQ * (NP - 1) + q - 1];
-      g[0] = fma(r.x, gL, -(r.y * g[0]));
-      v[0] = fma(r.x, vL, -(r.y * v[0]));
-    }
-  }
-}
-
-template <int NQ, int MINB>
-__global__ void __launch_bounds__(64 * NQ, MINB)
-svd64_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
-             int64_t batch, int* sweeps_out, int* fail_out) {
-  constexpr int N = 64, LD = kSvd64LD, SL = 64 / NQ, RL = 32 / NQ, NW = 2 * NQ, T = 64 * NQ;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* Gs = reinterpret_cast<double*>(smem_raw);
-  double* Vs = Gs + N * LD;
-  double* sq = Vs + N * LD;
-  double* dpart = sq + N;                                          // [NW][64]
-  double2* cs = reinterpret_cast<double2*>(dpart + kSvdR_DPART);   // [2][32]
-  double* nslot = reinterpret_cast<double*>(cs + 64);              // [64] cached |g_slot|^2
-  int* perm = reinterpret_cast<int*>(nslot + N);
-  int* zero_flag = perm + N;
-  int* done_flag = zero_flag + N;
-  int* flags = done_flag + N;                                      // [0] = "some pair was rotated in this sweep"
-
-  const int64_t m = blockIdx.x;
-  if (m >= batch) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = lane / RL, rl = lane % RL, row = RL * warp + rl;
-  const double* a_in = A + m * (N * N) + row * N + SL * q;
-
-  double g[SL], v[SL];
-#pragma unroll
-  for (int s = 0; s < SL; s += 2) {
-    const double2 t = ldg2_stream(a_in + s);
-    g[s] = t.x;
-    g[s + 1] = t.y;
-  }
-#pragma unroll
-  for (int s = 0; s < SL; s++) v[s] = (SL * q + s == row) ? 1.0 : 0.0;
-  if (tid == 0) flags[0] = 0;
-
-  const double tol2 = (N * kEps) * (N * kEps);
-  int sweeps = 0;
-  bool converged = false;
-  while (sweeps < kMaxSweeps && !converged) {
-    sweeps++;
-    // ---- exact slot norms at the start of the sweep ----
-    {
-      double n2[SL];
-#pragma unroll
-      for (int s = 0; s < SL; s++) n2[s] = g[s] * g[s];
-      halve_down<SL, 2>(n2, rl, RL / 2);
-      dpart[warp * 64 + SL * q + 2 * rl] = n2[0];  // slots SL*q + 2rl + {0,1}
-      dpart[warp * 64 + SL * q + 2 * rl + 1] = n2[1];
-      __syncthreads();
-      if (tid < N) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) t += dpart[w * 64 + tid];
-        nslot[tid] = t;
-      }
-      __syncthreads();
-    }
-#pragma unroll 1
-    for (int sp2 = 0; sp2 < N / 2; sp2++) {
-      svd64_step<NQ, false>(g, v, dpart, cs, nslot, flags, warp, lane, rl, q, (2 * sp2) % NW, tol2);
-      svd64_step<NQ, true>(g, v, dpart, cs + 32, nslot, flags, warp, lane, rl, q, (2 * sp2 + 1) % NW, tol2);
-    }
-    __syncthreads();
-    converged = (flags[0] == 0);
-    __syncthreads();
-    if (tid == 0) flags[0] = 0;
-  }
-  if (tid == 0) {
-    if (sweeps_out) atomicMax(sweeps_out, sweeps);
-    if (!converged && fail_out) atomicExch(fail_out, 1);
-  }
-
-  // ---- registers -> column-major shared memory, then the common epilogue ----
-#pragma unroll
-  for (int s = 0; s < SL; s++) {
-    Gs[(SL * q + s) * LD + row] = g[s];
-    Vs[(SL * q + s) * LD + row] = v[s];
-  }
-  __syncthreads();
-  svd64_epilogue<T>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
-}
-
-// ------------------------------------------------------------------------------------------------
-// 64x64, register-resident, decoupled: warps 0-3 own G (half rows), warps 4-7 own V (half rows).
-// Only the G warps are on the critical path of a step (dot products -> parameters -> rotate G); the V warps
-// consume the (c, s) of each step from a two-deep ring in shared memory and apply them one or two steps later,
-// filling the FP64 pipe while the G warps wait on shuffles, rsqrt latency and their own barriers.
-// Hand-shakes use named hardware barriers (bar.sync / bar.arrive):
-//   id 1, 2 : G-internal (partials visible / parameters visible), 128 threads
-//   id 3, 4 : ring slot 0/1 "ready"  (128 G threads arrive, 128 V threads wait), 256
-//   id 5, 6 : ring slot 0/1 "free"   (128 V threads arrive, 128 G threads wait), 256
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-template <bool STEP_B>
-__device__ __forceinline__ void rotate_half(double (&x)[32], const double2* cs_slot, int q, int lane) {
-  // half-row layout: lane = 16q + rl, slots 32q .. 32q+31; pair i = 16q + j at cs index 2j + q
-  if (!STEP_B) {
-#pragma unroll
-    for (int j = 0; j < 16; j++) { const double2 r = cs_slot[2 * j + q]; rot_swap(x[2 * j], x[2 * j + 1], r.x, r.y); }
-  } else {
-    const double xR0 = __shfl_down_sync(kFull, x[0], 16);
-    const double xL = __shfl_up_sync(kFull, x[31], 16);
-#pragma unroll
-    for (int j = 0; j < 15; j++) { const double2 r = cs_slot[2 * j + q]; rot_swap(x[2 * j + 1], x[2 * j + 2], r.x, r.y); }
-    if (q == 0) { const double2 r = cs_slot[30]; x[31] = fma(r.y, x[31], r.x * xR0); }        // pair 15 = (31 | 32)
-    else        { const double2 r = cs_slot[30]; x[0] = fma(r.x, xL, -(r.y * x[0])); }
-  }
-}
-
-template <bool STEP_B>
-__device__ __forceinline__ void svd64d_gstep(double (&g)[32], double* dpart, double2* cs_slot, double* nslot, int* flags,
-                                             int warp, int lane, int rl, int q, int pw, int slot, double tol2) {
-  constexpr int N = 64;
-  double pd[16];
-  if (!STEP_B) {
-#pragma unroll
-    for (int j = 0; j < 16; j++) pd[j] = g[2 * j] * g[2 * j + 1];
-  } else {
-    const double gR0 = __shfl_down_sync(kFull, g[0], 16);
-#pragma unroll
-    for (int j = 0; j < 15; j++) pd[j] = g[2 * j + 1] * g[2 * j + 2];
-    pd[15] = (q == 0) ? g[31] * gR0 : 0.0;
-  }
-  halve_down<16, 1>(pd, rl, 8);
-  dpart[warp * 64 + 16 * q + rl] = pd[0];  // pair 16q + rl, rows of this warp
-  bar_sync(1, 128);
-  bar_sync(5 + slot, 256);                  // the V warps are done with this ring slot
-  if (warp == pw) {
-    const int i = lane;
-    const double d = (dpart[i] + dpart[64 + i]) + (dpart[128 + i] + dpart[192 + i]);
-    const int sp = STEP_B ? 2 * i + 1 : 2 * i, sqq = sp + 1;
-    const bool have = sqq < N;
-    const double na = nslot[sp], nb = have ? nslot[sqq] : 0.0;
-    double c = 1.0, s = 0.0;
-    if (have && d * d > tol2 * na * nb) {
-      const double num = nb - na, den = 2.0 * d;
-      const double rh = rsqrt(fma(num, num, den * den));
-      const double c2 = fabs(num) * rh, s2 = fabs(den) * rh;
-      const double hc = fma(0.5, c2, 0.5);
-      const double rc = rsqrt(hc);
-      c = hc * rc;
-      s = 0.5 * s2 * rc;
-      if ((num < 0.0) != (den < 0.0)) s = -s;
-      const double cc = c * c, ss = s * s, csd = 2.0 * c * s * d;
-      nslot[sp] = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);
-      nslot[sqq] = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);
-      flags[0] = 1;
-    } else if (have) {
-      nslot[sp] = nb;
-      nslot[sqq] = na;
-    }
-    cs_slot[2 * (i & 15) + (i >> 4)] = make_double2(c, s);
-  }
-  bar_sync(2, 128);
-  bar_arrive(3 + slot, 256);                // parameters of this step are published
-  rotate_half<STEP_B>(g, cs_slot, q, lane);
-}
-
-__global__ void __launch_bounds__(256, 2)
-svd64d_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
-              int64_t batch, int* sweeps_out, int* fail_out) {
-  constexpr int N = 64, LD = kSvd64LD;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* Gs = reinterpret_cast<double*>(smem_raw);
-  double* Vs = Gs + N * LD;
-  double* sq = Vs + N * LD;
-  double* dpart = sq + N;                                          // [4][64]
-  double2* cs = reinterpret_cast<double2*>(dpart + kSvdR_DPART);   // ring: [2][32]
-  double* nslot = reinterpret_cast<double*>(cs + 64);
-  int* perm = reinterpret_cast<int*>(nslot + N);
-  int* zero_flag = perm + N;
-  int* done_flag = zero_flag + N;
-  int* flags = done_flag + N;  // [0] rotated in this sweep, [1] continue flag for the V warps
-
-  const int64_t m = blockIdx.x;
-  if (m >= batch) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool is_g = warp < 4;
-  const int gw = warp & 3;                       // warp index inside its group
-  const int q = lane >> 4, rl = lane & 15, row = 16 * gw + rl;
-  double x[32];                                  // half a row of G (G warps) or of V (V warps)
-  if (is_g) {
-    const double* a_in = A + m * (N * N) + row * N + 32 * q;
-#pragma unroll
-    for (int s = 0; s < 32; s += 2) {
-      const double2 t = ldg2_stream(a_in + s);
-      x[s] = t.x;
-      x[s + 1] = t.y;
-    }
-  } else {
-#pragma unroll
-    for (int s = 0; s < 32; s++) x[s] = (32 * q + s == row) ? 1.0 : 0.0;
-  }
-  if (tid == 0) { flags[0] = 0; flags[1] = 1; }
-  __syncthreads();
-
-  const double tol2 = (N * kEps) * (N * kEps);
-  int sweeps = 0;
-  bool converged = false;
-  while (sweeps < kMaxSweeps && !converged) {
-    sweeps++;
-    if (is_g) {
-      // exact slot norms at the start of the sweep (G warps only)
-      double n2[32];
-#pragma unroll
-      for (int s = 0; s < 32; s++) n2[s] = x[s] * x[s];
-      halve_down<32, 2>(n2, rl, 8);
-      dpart[gw * 64 + 32 * q + 2 * rl] = n2[0];
-      dpart[gw * 64 + 32 * q + 2 * rl + 1] = n2[1];
-      bar_sync(1, 128);
-      if (tid < N) nslot[tid] = (dpart[tid] + dpart[64 + tid]) + (dpart[128 + tid] + dpart[192 + tid]);
-      bar_sync(2, 128);
-#pragma unroll 1
-      for (int sp2 = 0; sp2 < N / 2; sp2++) {
-        svd64d_gstep<false>(x, dpart, cs, nslot, flags, gw, lane, rl, q, (2 * sp2) & 3, 0, tol2);
-        svd64d_gstep<true>(x, dpart, cs + 32, nslot, flags, gw, lane, rl, q, (2 * sp2 + 1) & 3, 1, tol2);
-      }
-    } else {
-      bar_arrive(5, 256);  // both ring slots start out free
-      bar_arrive(6, 256);
-#pragma unroll 1
-      for (int sp2 = 0; sp2 < N / 2; sp2++) {
-        bar_sync(3, 256);
-        rotate_half<false>(x, cs, q, lane);
-        if (sp2 + 1 < N / 2) bar_arrive(5, 256);
-        bar_sync(4, 256);
-        rotate_half<true>(x, cs + 32, q, lane);
-        if (sp2 + 1 < N / 2) bar_arrive(6, 256);
-      }
-    }
-    __syncthreads();
-    converged = (flags[0] == 0);
-    __syncthreads();
-    if (tid == 0) flags[0] = 0;
-  }
-  if (tid == 0) {
-    if (sweeps_out) atomicMax(sweeps_out, sweeps);
-    if (!converged && fail_out) atomicExch(fail_out, 1);
-  }
-  double* dst = is_g ? Gs : Vs;
-#pragma unroll
-  for (int s = 0; s < 32; s++) dst[(32 * q + s) * LD + row] = x[s];
-  __syncthreads();
-  svd64_epilogue<256>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
-}
-
 // ------------------------------------------------------------------------------------------------
 // 64x64, register-resident, column-block per warp ("CB").
 //
-// The kernels above split the ROWS of a column over several warps, so every step needs a cross-warp reduction
-// (smem + CTA barrier) and a single parameter warp that all others wait for.  Here a warp owns 16 whole columns
+// Design history (profiles/): with G and V in shared memory a rotated pair moves 4 KiB through smem and the
+// kernel is smem-bandwidth bound (svd64_smem_kernel above, 40 ms on C5); with rows split over several warps every step
+// needs a cross-warp reduction, two CTA barriers and one parameter warp everybody waits for (29 ms).  Here every
+// rotation is thread-local and a step needs no shared memory or barrier: a warp owns 16 whole columns
 // (slots): lane l holds rows l and l+32 of G and of V for those 16 slots.  The 8 dot products of a step are
 // reduced inside the warp (recursive halving over lane bits 4,3,2, then a 2-stage butterfly), the 4-lane group g
 // computes the rotation of pair g, and the 8 (c, s) are gathered with shuffles: no shared memory, no barrier and no
@@ -1078,12 +704,7 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(svd64_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64cb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64CbSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64cb_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64CbSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64RegSmem);
+      cudaError_t e = cudaFuncSetAttribute(svd64cb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64CbSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64Smem);
       if (e != cudaSuccess) return e;
       attr_set[dev] = true;
@@ -1091,15 +712,10 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     static int variant = -1;
     if (variant < 0) {
       const char* ev = getenv("ND4B_SVD_VARIANT");
-      variant = ev ? atoi(ev) : 5;
+      variant = ev ? atoi(ev) : 0;  // 1 = the shared-memory baseline kernel (kept for A/B profiling)
     }
     if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else if (variant == 5) svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else if (variant == 6) svd64cb_kernel<3><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else if (variant == 3) svd64d_kernel<<<(unsigned)batch, 256, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else if (variant == 2) svd64_kernel<2, 3><<<(unsigned)batch, 128, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else if (variant == 4) svd64_kernel<2, 2><<<(unsigned)batch, 128, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else svd64_kernel<4, 2><<<(unsigned)batch, 256, kSvd64RegSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    else svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
     return cudaGetLastError();
   }
   const size_t need = svd_workspace_bytes(batch, rows, cols);
