@@ -186,6 +186,23 @@ qr64x32_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __r
       a[i][2 * jp + 1] = v.y;
     }
 
+  // scale guard (see pow2_prescale): one max-reduction per matrix, a multiplication only for extreme magnitudes
+  double amax = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) amax = fmax(amax, fabs(a[i][j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, shfl_xor(amax, o));
+  const double pre = pow2_prescale(amax);
+  if (pre != 1.0) {  // warp-uniform
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[i][j] *= pre;
+  }
+  const double post = 1.0 / pre;  // exact (power of two)
+
   double mytau = 0.0, mysgn = 1.0;  // lane k keeps tau_k and the sign of beta_k
 
   qr_block<0, false>(a, lane, r, c, mytau, mysgn);
@@ -199,7 +216,7 @@ qr64x32_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __r
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int row = r + 8 * i;
-      const double sg = shfl(mysgn, row);
+      const double sg = shfl(mysgn, row) * post;
 #pragma unroll
       for (int jp = 0; jp < 4; jp++) {
         const int col = 8 * jp + 2 * c;
@@ -262,8 +279,21 @@ qr_generic_kernel(const double* __restrict__ A, double* __restrict__ Q, double* 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kQrGenThreads / 32;
 
-  for (int64_t e = tid; e < rc; e += kQrGenThreads) W[e] = a_in[e];
+  double amax = 0.0;
+  for (int64_t e = tid; e < rc; e += kQrGenThreads) { const double x = a_in[e]; W[e] = x; amax = fmax(amax, fabs(x)); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(kFull, amax, o));
+  if (lane == 0) red[warp] = amax;
   __syncthreads();
+  amax = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) amax = fmax(amax, red[w]);
+  const double pre = pow2_prescale(amax), post = 1.0 / pre;
+  __syncthreads();
+  if (pre != 1.0) {
+    for (int64_t e = tid; e < rc; e += kQrGenThreads) W[e] *= pre;
+    __syncthreads();
+  }
 
   for (int k = 0; k < L; k++) {
     double part = 0.0;
@@ -295,7 +325,7 @@ qr_generic_kernel(const double* __restrict__ A, double* __restrict__ Q, double* 
   // R
   for (int64_t e = tid; e < (int64_t)L * cols; e += kQrGenThreads) {
     const int i = (int)(e / cols), j = (int)(e % cols);
-    rr[e] = (j >= i) ? W[(int64_t)i * cols + j] : 0.0;
+    rr[e] = (j >= i) ? W[(int64_t)i * cols + j] * post : 0.0;
   }
   // Q = H_0 ... H_{L-1} [I_L; 0]  (rows x L), backward accumulation
   for (int64_t e = tid; e < (int64_t)rows * L; e += kQrGenThreads) {

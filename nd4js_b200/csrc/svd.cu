@@ -126,7 +126,8 @@ constexpr size_t kSvd64Smem = sizeof(double) * (2 * 64 * kSvd64LD + 64) + sizeof
 // (zero columns completed to an orthonormal basis) and writes U, sv, V.  Called by all 256 threads after a barrier.
 template <int T>
 __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* sq, int* perm, int* zero_flag, int* done_flag,
-                                               double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V, int64_t m) {
+                                               double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V, int64_t m,
+                                               double sigma_scale) {
   constexpr int N = 64, LD = kSvd64LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NG = T / 8;  // 8-lane groups in the CTA; each handles columns P, P+NG, ...
@@ -186,7 +187,7 @@ __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* s
     u_out[e] = Gs[perm[l] * LD + i];   // U[i][l]
     v_out[e] = Vs[perm[i] * LD + l];   // V[l'][j] with l' = i, j = l
   }
-  if (tid < N) SV[m * N + tid] = zero_flag[perm[tid]] ? 0.0 : sq[perm[tid]];
+  if (tid < N) SV[m * N + tid] = zero_flag[perm[tid]] ? 0.0 : sq[perm[tid]] * sigma_scale;
 }
 
 __global__ void __launch_bounds__(kSvd64Threads, 3)
@@ -273,7 +274,7 @@ svd64_smem_kernel(const double* __restrict__ A, double* __restrict__ U, double* 
     if (!converged && fail_out) atomicExch(fail_out, 1);
   }
 
-  svd64_epilogue<kSvd64Threads>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
+  svd64_epilogue<kSvd64Threads>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m, 1.0);
 }
 
 // v[0..N/2) <- v[keep half] + partner's contribution; lanes with `bit` set keep the upper half
@@ -470,6 +471,20 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
   }
   st.xg0 = st.xg1 = st.xv0 = st.xv1 = st.xn = 0.0;
   st.xd = st.xdi = 1.0;
+  // scale guard (see pow2_prescale): squared column norms must neither overflow nor flush to zero
+  double amax = 0.0;
+#pragma unroll
+  for (int s = 0; s < 16; s++) amax = fmax(amax, fmax(fabs(st.g0[s]), fabs(st.g1[s])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, shfl_xor(amax, o));
+  if (lane == 0) sq[warp] = amax;
+  __syncthreads();
+  amax = fmax(fmax(sq[0], sq[1]), fmax(sq[2], sq[3]));
+  const double pre = pow2_prescale(amax);
+  if (pre != 1.0) {
+#pragma unroll
+    for (int s = 0; s < 16; s++) { st.g0[s] *= pre; st.g1[s] *= pre; }
+  }
 
   const double tol2 = (N * kEps) * (N * kEps);
   int sweeps = 0;
@@ -547,7 +562,7 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
     Vs[(16 * warp + s) * LD + lane + 32] = st.v1[s];
   }
   __syncthreads();
-  svd64_epilogue<128>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m);
+  svd64_epilogue<128>(Gs, Vs, sq, perm, zero_flag, done_flag, U, SV, V, m, 1.0 / pre);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -579,9 +594,20 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   constexpr int NW = kSvdGenThreads / 32;
 
   // G = A (tall: Gt[j][i] = A[i][j]) or A^T (wide: Gt[j][i] = A[j][i])
+  __shared__ double red_max[NW];
+  double amax = 0.0;
+  for (int64_t e = tid; e < (int64_t)rows * cols; e += kSvdGenThreads) amax = fmax(amax, fabs(a_in[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(kFull, amax, o));
+  if (lane == 0) red_max[warp] = amax;
+  __syncthreads();
+  amax = 0.0;
+  for (int w = 0; w < NW; w++) amax = fmax(amax, red_max[w]);
+  const double pre = pow2_prescale(amax), post = 1.0 / pre;   // scale guard, exact power of two
   for (int64_t e = tid; e < (int64_t)rows * cols; e += kSvdGenThreads) {
-    if (wide) Gt[e] = a_in[e];
-    else { const int i = (int)(e / cols), j = (int)(e % cols); Gt[(size_t)j * mm + i] = a_in[e]; }
+    const double x = a_in[e] * pre;
+    if (wide) Gt[e] = x;
+    else { const int i = (int)(e / cols), j = (int)(e % cols); Gt[(size_t)j * mm + i] = x; }
   }
   for (int64_t e = tid; e < (int64_t)n * n; e += kSvdGenThreads) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
   __syncthreads();
@@ -686,7 +712,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
     const int l = (int)(e / cols), j = (int)(e % cols);
     v_out[e] = vsrc[(size_t)perm[l] * vld + j];
   }
-  for (int l = tid; l < n; l += kSvdGenThreads) SV[m * n + l] = zero_flag[perm[l]] ? 0.0 : sig[perm[l]];
+  for (int l = tid; l < n; l += kSvdGenThreads) SV[m * n + l] = zero_flag[perm[l]] ? 0.0 : sig[perm[l]] * post;
 }
 
 size_t svd_workspace_bytes(int64_t batch, int rows, int cols) {
