@@ -35,7 +35,7 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
                       double* work, size_t work_bytes);
 
 // rows=64, cols=32 on the FP64 tensor pipe (qr_blocked.cu); no alignment requirement beyond 8 bytes
-cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch);
+cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int variant);
 
 size_t svd_workspace_bytes(int64_t batch, int rows, int cols);
 // sweeps: device int32 (atomicMax).  fail: device int32 set to 1 if some matrix hit the sweep limit.

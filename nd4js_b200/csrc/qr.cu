@@ -365,9 +365,9 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
     static int variant = -1;
     if (variant < 0) {
       const char* ev = getenv("ND4B_QR_VARIANT");
-      variant = ev ? atoi(ev) : 0;  // 1 = the unblocked register kernel (kept for A/B profiling)
+      variant = ev ? atoi(ev) : 0;  // 1 = the unblocked register kernel, 2 = the blocked one at two CTAs per SM (A/B profiling)
     }
-    if (variant != 1 || !aligned) return launch_qr64x32_blocked(s, A, Q, R, batch);
+    if (variant != 1 || !aligned) return launch_qr64x32_blocked(s, A, Q, R, batch, variant);
     // 222 registers -> 2 CTAs of 4 warps per SM.  Capping registers for 3 CTAs (168) or using 1-/2-warp CTAs was
     // measured slower (spills): 2.05 / 2.27 / 2.20 ms vs 1.86 ms on C4.
     qr64x32_kernel<kQrWarps, 2><<<(unsigned)((batch + kQrWarps - 1) / kQrWarps), kQrWarps * 32, 0, s>>>(A, Q, R, batch);

@@ -7,7 +7,7 @@
 // With that layout every product of the blocked algorithm is a chain of DMMA.8x8x4 whose fragments are the registers
 // themselves (an accumulator tile X[g][2t+e] is the A fragment pair of a following product, k <-> 2t+e):
 //   panel p (columns 8p..8p+7, one column per quad):  unblocked Householder, 8 steps; a step broadcasts the pivot
-//       column from its quad (shuffles), forms all dot products with it (the pivot quad's is the squared norm) and
+//       column through shared memory, forms all dot products with it (the pivot quad's is the squared norm) and
 //       applies the rank-1 update — reflector scalars need one rsqrt and one reciprocal.
 //   T of the compact WY form (H_1..H_8 = I - V T V^T):  G = V^T V by DMMA (both fragments are the same register),
 //       T^-1 = striu(G) + diag(1/tau)  =>  T = (I+N)^-1 diag(tau), N = diag(tau) striu(G) nilpotent, and
@@ -20,14 +20,32 @@
 #include "common.cuh"
 #include "kernels.h"
 
+// Phase profiling hook for tools/micro/qr_phase_prof.cu (which includes this file with QB_PROFILE defined).
+#ifdef QB_PROFILE
+__device__ unsigned long long qb_prof[16];
+#define QB_MARK(i)                                                                              \
+  do {                                                                                          \
+    const long long n_ = clock64();                                                             \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&qb_prof[i], (unsigned long long)(n_ - qb_tm));      \
+    qb_tm = n_;                                                                                 \
+  } while (0)
+#else
+#define QB_MARK(i) do { } while (0)
+#endif
+
 namespace nd4b {
 
 namespace {
 
-constexpr int kQbWarps = 4;
-constexpr int kVS = 34;                                   // row stride (doubles) of the per-warp V store
-constexpr int kQbWarpDoubles = 64 * kVS + 4 * 64;         // V store + the four T's (accumulator layout, 2 per lane)
-constexpr size_t kQbSmem = sizeof(double) * kQbWarpDoubles * kQbWarps;
+// Per-warp shared memory: the clean V panels (panel p: rows 8p..63, 8 columns, row-major, no padding), the four T's
+// (accumulator layout, 2 doubles per lane) and the pivot-column buffers: 16.6 KiB, so that 12 warps fit one SM.
+__host__ __device__ constexpr int v_off(int p) { return 8 * (64 * p - 4 * p * (p - 1)); }  // 0, 512, 960, 1344
+constexpr int kVDoubles = 1664;
+constexpr int kXsOff = kVDoubles + 4 * 64;       // two pivot-column buffers (+ 64 spare)
+constexpr int kMbarOff = kXsOff + 3 * 64;        // mbarrier of the bulk load
+constexpr int kQbWarpDoubles = kMbarOff + 16;    // 2128 doubles = 17 024 B (a multiple of 128 B)
+// The first 2048 doubles double as the landing zone of the bulk load of A (TMA, 16 KiB) and as the staging tile of the
+// bulk store of Q: 8-byte per-lane global accesses in the fragment layout cost 4 L1 tag look-ups per instruction.
 
 struct Acc { double x, y; };  // 8x8 tile in accumulator layout: x = M[g][2t], y = M[g][2t+1]
 
@@ -39,65 +57,136 @@ __device__ __forceinline__ Acc mm8(const Acc& X, const Acc& YT) {
   return o;
 }
 
+// Approximate reciprocal square root / reciprocal (MUFU.RSQ64H / MUFU.RCP64H, about 20 good bits); refined below.
+__device__ __forceinline__ double rsqrt_approx(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ double rcp_approx(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
+// 16-byte shared-memory load that the compiler may not merge with an earlier load of the same address (the pivot column
+// is read twice per step instead of being held in 32 registers across the scalar chain).
+__device__ __forceinline__ double2 lds2_again(const double* p) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// One lane: bulk copy (TMA, UBLKCP) of `bytes` from global to shared memory, completion on an mbarrier it initialises.
+__device__ __forceinline__ void bulk_load_start(void* dst, const void* src, unsigned bytes, void* mbar) {
+  const unsigned mb = smem_u32(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
+__device__ __forceinline__ void bulk_load_wait(void* mbar) {
+  const unsigned mb = smem_u32(mbar);
+  asm volatile("{\n.reg .pred p;\nQB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@!p bra QB_WAIT;\n}" ::"r"(mb) : "memory");
+}
+// One lane: bulk copy shared -> global; returns when the shared source has been read.
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Predicated 16-byte shared store: lanes with pred == false issue nothing (no divergence, no wavefronts).
+__device__ __forceinline__ void sts2_if(bool pred, double* p, double x, double y) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.shared.v2.f64 [%1], {%2,%3};\n}"
+               ::"r"((unsigned)pred), "r"(smem_u32(p)), "d"(x), "d"(y) : "memory");
+}
+
 // ---- panel P: unblocked Householder on columns 8P..8P+7 (my column: 8P+g), rows >= 8P ----
-template <int P>
-__device__ __forceinline__ void qb_panel(double (&a)[4][8][2], int lane, int g, int t, double& tau_q, double& sgn_q) {
+// xs: two 64-double buffers; the pivot column (rows above the pivot row zeroed) is published there by its quad and
+// read back by every lane with broadcast 16-byte loads (a shuffle broadcast of 16 doubles costs 32 SHFL per step).
+// The step is one dependent chain (dots -> |x|^2 -> reflector scalars -> update), so the scalar part is written for
+// depth: branch-free, 1/sqrt and 1/v0 refined from overlapping 20-bit estimates.
+template <int P, bool REREAD>
+__device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int lane, int g, int t, double& tau_q, double& sgn_q) {
   double inv_q = 0.0;
   tau_q = 0.0;
   sgn_q = 1.0;
+  if (g == 0) {
+#pragma unroll
+    for (int j = P; j < 8; j++) *reinterpret_cast<double2*>(xs + 8 * j + 2 * t) = make_double2(a[P][j][0], a[P][j][1]);
+  }
 #pragma unroll 1
   for (int kk = 0; kk < 8; kk++) {
-    const int src = 4 * kk + t;
+    const double* xb = xs + 64 * (kk & 1);
+    __syncwarp();
+    const double x0 = xb[8 * P + kk];  // pivot element
     double x[8][2];
+    double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;  // four independent chains
 #pragma unroll
     for (int j = P; j < 8; j++) {
-      x[j][0] = shfl(a[P][j][0], src);
-      x[j][1] = shfl(a[P][j][1], src);
+      const double2 v = *reinterpret_cast<const double2*>(xb + 8 * j + 2 * t);
+      x[j][0] = v.x;
+      x[j][1] = v.y;
+      if ((j - P) & 1) { d01 = fma(v.x, a[P][j][0], d01); d11 = fma(v.y, a[P][j][1], d11); }
+      else { d00 = fma(v.x, a[P][j][0], d00); d10 = fma(v.y, a[P][j][1], d10); }
     }
-    // rows above the pivot row k = 8P+kk hold finished R entries
-    x[P][0] = (2 * t >= kk) ? x[P][0] : 0.0;
-    x[P][1] = (2 * t + 1 >= kk) ? x[P][1] : 0.0;
-    double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-    for (int j = P; j < 8; j++) {
-      d0 = fma(x[j][0], a[P][j][0], d0);
-      d1 = fma(x[j][1], a[P][j][1], d1);
-    }
-    double d = d0 + d1;
+    double d = (d00 + d01) + (d10 + d11);
+    // |x|^2 over rows >= k: the four partial sums of the pivot quad, fetched in parallel
+    const double s = (shfl(d, 4 * kk) + shfl(d, 4 * kk + 1)) + (shfl(d, 4 * kk + 2) + shfl(d, 4 * kk + 3));
     d += shfl_xor(d, 1);
     d += shfl_xor(d, 2);
-    const double s = shfl(d, 4 * kk);  // |x|^2 (rows >= k) from the pivot quad
     const int e0 = kk & 1, t0 = kk >> 1;
-    const int qsrc = (lane & ~3) | t0;
-    const double x0 = shfl(e0 ? x[P][1] : x[P][0], qsrc);         // pivot element
-    const double akj = shfl(e0 ? a[P][P][1] : a[P][P][0], qsrc);  // my column's element in the pivot row
-    double beta = 0.0, tau = 0.0, v0 = 0.0, inv_v0 = 0.0;
-    if (s != 0.0) {  // warp-uniform; s == 0: H = I
-      const double rn = rsqrt(s);
-      const double nrm = s * rn;
-      beta = -copysign(nrm, x0);
-      tau = fma(fabs(x0), rn, 1.0);
-      v0 = x0 - beta;
-      inv_v0 = 1.0 / v0;
-    }
-    // v = x~/v0 with x~ = (v0; x below), w = v^T a = (d - beta*akj)/v0, a -= tau*w*v
-    const double w = (d - beta * akj) * inv_v0;
-    const double f = (g > kk) ? -(tau * w) * inv_v0 : 0.0;
-    if (t == t0) {
-      if (e0) x[P][1] = v0; else x[P][0] = v0;
-    }
+    const double akj = shfl(e0 ? a[P][P][1] : a[P][P][0], (lane & ~3) | t0);  // my column's element in the pivot row
+    const bool ok = s > 0x1p-900;  // else a (numerically) zero column: H = I
+    const double ss = ok ? s : 1.0;
+    // nrm = sqrt(ss), rn = 1/nrm by one cubic step from the 20-bit estimate y0; 1/v0 by Newton from an estimate taken at
+    // the approximate v0 (the two special-function latencies overlap)
+    const double y0 = rsqrt_approx(ss);
+    const double sy = ss * y0;
+    const double r0 = rcp_approx(x0 + copysign(sy, x0));
+    const double e = fma(-sy, y0, 1.0);
+    const double pe = fma(0.375, e, 0.5);
+    const double nrm = fma(sy * e, pe, sy);
+    const double rn = fma(y0 * e, pe, y0);
+    const double cn = copysign(nrm, x0);  // -beta
+    const double v0 = x0 + cn;
+    const double tau = fma(fabs(x0), rn, 1.0);
+    const double r1 = fma(fma(-v0, r0, 1.0), r0, r0);
+    const double e2 = fma(-v0, r1, 1.0);  // ~2^-40
+    // v = x~/v0 with x~ = (v0; x below), w = v^T a = (d - beta*akj)/v0, a -= tau*w*v = a + f x~, f = -tau (d - beta*akj)/v0^2
+    const double tc = (ok && g > kk) ? tau * fma(cn, akj, d) : 0.0;
+    const double tr = tc * (r1 * r1);
+    const double f = fma(-tr, e2 + e2, -tr);  // 1/v0^2 = r1^2 (1 + 2 e2) to working precision
+    const bool prow = (t == t0);
 #pragma unroll
     for (int j = P; j < 8; j++) {
-      a[P][j][0] = fma(f, x[j][0], a[P][j][0]);
-      a[P][j][1] = fma(f, x[j][1], a[P][j][1]);
-    }
-    if (g == kk) {
-      tau_q = tau;
-      inv_q = inv_v0;
-      sgn_q = (beta < 0.0) ? -1.0 : 1.0;
-      if (t == t0) {
-        if (e0) a[P][P][1] = beta; else a[P][P][0] = beta;
+      double2 v = REREAD ? lds2_again(xb + 8 * j + 2 * t) : make_double2(x[j][0], x[j][1]);
+      if (j == P) {  // x~: v0 in the pivot row (branch-free)
+        v.x = (prow && !e0) ? v0 : v.x;
+        v.y = (prow && e0) ? v0 : v.y;
       }
+      a[P][j][0] = fma(f, v.x, a[P][j][0]);
+      a[P][j][1] = fma(f, v.y, a[P][j][1]);
+    }
+    {  // the next pivot quad publishes its column, rows above its pivot row zeroed (predicated stores)
+      const bool nxt = (g == kk + 1);
+      double* xn = xs + 64 * ((kk + 1) & 1);
+      sts2_if(nxt, xn + 8 * P + 2 * t, (2 * t > kk) ? a[P][P][0] : 0.0, (2 * t + 1 > kk) ? a[P][P][1] : 0.0);
+#pragma unroll
+      for (int j = P + 1; j < 8; j++) sts2_if(nxt, xn + 8 * j + 2 * t, a[P][j][0], a[P][j][1]);
+    }
+    {  // the pivot quad records its reflector (selects, no divergence)
+      const bool piv = (g == kk);
+      tau_q = piv ? (ok ? tau : 0.0) : tau_q;
+      inv_q = piv ? (ok ? fma(e2, r1, r1) : 0.0) : inv_q;
+      sgn_q = piv ? ((ok && cn > 0.0) ? -1.0 : 1.0) : sgn_q;
+      const double beta = ok ? -cn : 0.0;
+      a[P][P][0] = (piv && prow && !e0) ? beta : a[P][P][0];
+      a[P][P][1] = (piv && prow && e0) ? beta : a[P][P][1];
     }
   }
   // v = x / v0 below the diagonal (deferred: later steps never read a finished column)
@@ -159,7 +248,7 @@ __device__ __forceinline__ void qb_trailing(double (&a)[4][8][2], const double* 
     Z.y = -Z.y;
 #pragma unroll
     for (int j = P; j < 8; j++) {
-      const double2 v = *reinterpret_cast<const double2*>(vs + (8 * j + g) * kVS + 8 * P + 2 * t);
+      const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + 2 * t);
       dmma884(a[i][j][0], a[i][j][1], Z.x, v.x);
       dmma884(a[i][j][0], a[i][j][1], Z.y, v.y);
     }
@@ -179,11 +268,13 @@ __device__ __forceinline__ void qb_store_r(const double (&a)[4][8][2], double* _
   r_out[(row0 + 1) * 32 + col] = v1;
 }
 
-template <int P>
+template <int P, bool REREAD>
 __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, double* ts,
-                                           double* __restrict__ r_out, int lane, int g, int t, double post, double& sgn_p) {
+                                           double* __restrict__ r_out, int lane, int g, int t, double post, double& sgn_p,
+                                           long long& qb_tm) {
   double tau_q;
-  qb_panel<P>(a, lane, g, t, tau_q, sgn_p);
+  qb_panel<P, REREAD>(a, vs + kXsOff, lane, g, t, tau_q, sgn_p);
+  QB_MARK(2);
   const double s0 = shfl(sgn_p, 4 * (2 * t)) * post, s1 = shfl(sgn_p, 4 * (2 * t + 1)) * post;
   // R: diagonal block and the zero blocks left of it; then the head of the panel becomes the clean unit-lower V
   if (P > 0) qb_store_r<P, 0>(a, r_out, g, t, s0, s1);
@@ -194,19 +285,22 @@ __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, dou
   a[P][P][1] = (2 * t + 1 > g) ? a[P][P][1] : ((2 * t + 1 == g) ? 1.0 : 0.0);
 #pragma unroll
   for (int j = P; j < 8; j++) {
-    vs[(8 * j + 2 * t) * kVS + 8 * P + g] = a[P][j][0];
-    vs[(8 * j + 2 * t + 1) * kVS + 8 * P + g] = a[P][j][1];
+    vs[v_off(P) + (8 * (j - P) + 2 * t) * 8 + g] = a[P][j][0];
+    vs[v_off(P) + (8 * (j - P) + 2 * t + 1) * 8 + g] = a[P][j][1];
   }
+  QB_MARK(3);
   Acc T, TT;
   qb_make_t<P>(a, g, t, tau_q, T, TT);
   *reinterpret_cast<double2*>(ts + 64 * P + 2 * lane) = make_double2(T.x, T.y);
   __syncwarp();
+  QB_MARK(4);
   if (P < 3) {
     qb_trailing<P, P>(a, vs, g, t, TT);
     if (P < 1) qb_store_r<P, 1>(a, r_out, g, t, s0, s1);
     if (P < 2) qb_store_r<P, 2>(a, r_out, g, t, s0, s1);
     qb_store_r<P, 3>(a, r_out, g, t, s0, s1);
   }
+  QB_MARK(5);
 }
 
 template <int P>
@@ -217,7 +311,7 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
   // columns right of the panel: nonzero from row 8(P+1) on, filled from row 8P on by this update
   if (P < 3) qb_trailing<P, P + 1>(a, vs, g, t, T);
   // the panel's own columns: E_P - V_P (T_P L_P^T)
-  const double2 l = *reinterpret_cast<const double2*>(vs + (8 * P + g) * kVS + 8 * P + 2 * t);
+  const double2 l = *reinterpret_cast<const double2*>(vs + v_off(P) + g * 8 + 2 * t);
   Acc M = mm8(Acc{l.x, l.y}, T);  // (L_P T_P^T)[b][c] = M^T
   M.x = -M.x;
   M.y = -M.y;
@@ -225,7 +319,7 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
   for (int j = 0; j < P; j++) { a[P][j][0] = 0.0; a[P][j][1] = 0.0; }
 #pragma unroll
   for (int j = P; j < 8; j++) {
-    const double2 v = *reinterpret_cast<const double2*>(vs + (8 * j + g) * kVS + 8 * P + 2 * t);
+    const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + 2 * t);
     double q0 = (j == P && g == 2 * t) ? 1.0 : 0.0, q1 = (j == P && g == 2 * t + 1) ? 1.0 : 0.0;
     dmma884(q0, q1, M.x, v.x);
     dmma884(q0, q1, M.y, v.y);
@@ -234,33 +328,54 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
   }
 }
 
-__global__ void __launch_bounds__(kQbWarps * 32, 2)
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch) {
   extern __shared__ __align__(16) double qb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int64_t m = (int64_t)blockIdx.x * kQbWarps + warp;
-  if (m >= batch) return;  // warp-uniform; no block-level barriers below
+  const int64_t m = (int64_t)blockIdx.x * WARPS + warp;
+  if (m >= batch) return;  // warp-uniform; the kernel has no block-level barriers
   double* vs = qb_smem + warp * kQbWarpDoubles;
-  double* ts = vs + 64 * kVS;
+  double* ts = vs + kVDoubles;
   const double* a_in = A + m * 2048;
 
+  long long qb_tm = clock64();
+  (void)qb_tm;
   double a[4][8][2];
+  const bool bulk = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;  // kernel-uniform
+  if (bulk) {
+    if (lane == 0) bulk_load_start(vs, a_in, 16384, vs + kMbarOff);
+    __syncwarp();
+    bulk_load_wait(vs + kMbarOff);
 #pragma unroll
-  for (int j = 0; j < 8; j++)
+    for (int j = 0; j < 8; j++)
 #pragma unroll
-    for (int e = 0; e < 2; e++)
+      for (int e = 0; e < 2; e++)
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i][j][e] = ldg1_stream(a_in + (8 * j + 2 * t + e) * 32 + 8 * i + g);
+        for (int i = 0; i < 4; i++) a[i][j][e] = vs[(8 * j + 2 * t + e) * 32 + 8 * i + g];
+    __syncwarp();  // the landing zone becomes the V store
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i][j][e] = ldg1_stream(a_in + (8 * j + 2 * t + e) * 32 + 8 * i + g);
+  }
 
-  // scale guard (see pow2_prescale)
-  double amax = 0.0;
+  // scale guard (see pow2_prescale): only the binary exponent of the largest entry matters, so the maximum is taken over
+  // the high words as integers (no FP64 instructions) and reduced with one REDUX
+  unsigned hi = 0;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) amax = fmax(amax, fmax(fabs(a[i][j][0]), fabs(a[i][j][1])));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, shfl_xor(amax, o));
+    for (int j = 0; j < 8; j++) {
+      hi = max(hi, (unsigned)__double2hiint(a[i][j][0]) & 0x7fffffffu);
+      hi = max(hi, (unsigned)__double2hiint(a[i][j][1]) & 0x7fffffffu);
+    }
+  hi = __reduce_max_sync(kFull, hi);
+  const double amax = __hiloint2double((int)hi, 0);
   const double pre = pow2_prescale(amax);
   if (pre != 1.0) {
 #pragma unroll
@@ -272,38 +387,65 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
 
   double* r_out = R + m * 1024;
   double sgn[4];
-  qb_r_phase<0>(a, vs, ts, r_out, lane, g, t, post, sgn[0]);
-  qb_r_phase<1>(a, vs, ts, r_out, lane, g, t, post, sgn[1]);
-  qb_r_phase<2>(a, vs, ts, r_out, lane, g, t, post, sgn[2]);
-  qb_r_phase<3>(a, vs, ts, r_out, lane, g, t, post, sgn[3]);
+  QB_MARK(0);
+  qb_r_phase<0, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm);
+  qb_r_phase<1, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm);
+  qb_r_phase<2, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm);
+  qb_r_phase<3, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm);
 
   qb_q_phase<3>(a, vs, ts, lane, g, t);
   qb_q_phase<2>(a, vs, ts, lane, g, t);
   qb_q_phase<1>(a, vs, ts, lane, g, t);
   qb_q_phase<0>(a, vs, ts, lane, g, t);
+  QB_MARK(6);
 
   double* q_out = Q + m * 2048;
+  if (bulk) {
+    __syncwarp();  // every lane is done with the V store
 #pragma unroll
-  for (int j = 0; j < 8; j++)
+    for (int j = 0; j < 8; j++)
 #pragma unroll
-    for (int e = 0; e < 2; e++)
+      for (int e = 0; e < 2; e++)
 #pragma unroll
-      for (int i = 0; i < 4; i++) q_out[(8 * j + 2 * t + e) * 32 + 8 * i + g] = sgn[i] * a[i][j][e];
+        for (int i = 0; i < 4; i++) vs[(8 * j + 2 * t + e) * 32 + 8 * i + g] = sgn[i] * a[i][j][e];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) bulk_store(q_out, vs, 16384);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) q_out[(8 * j + 2 * t + e) * 32 + 8 * i + g] = sgn[i] * a[i][j][e];
+  }
+  QB_MARK(7);
 }
 
 }  // namespace
 
-cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch) {
+template <int WARPS, int MINB>
+static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch) {
   static bool attr_set[64] = {false};
+  constexpr size_t smem = sizeof(double) * kQbWarpDoubles * WARPS;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQbSmem);
+    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  qr64x32_blocked_kernel<<<(unsigned)((batch + kQbWarps - 1) / kQbWarps), kQbWarps * 32, kQbSmem, s>>>(A, Q, R, batch);
+  qr64x32_blocked_kernel<WARPS, MINB><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(A, Q, R, batch);
   return cudaGetLastError();
+}
+
+// variant 2: two CTAs per SM (216 registers, no spills, pivot column kept in registers) instead of three (168 registers,
+// idle column blocks parked in local memory around the panel loops): 1.43 vs 1.38 ms on C4.  Phase-locking the warps of
+// a sub-partition with named barriers (so that no DMMA stream runs beside a panel chain) was measured slower (1.55-1.70 ms):
+// the panel chains of the locked warps then collide on the shared-memory pipe instead.
+cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int variant) {
+  if (variant == 2) return qb_launch<4, 2>(s, A, Q, R, batch);
+  return qb_launch<4, 3>(s, A, Q, R, batch);
 }
 
 }  // namespace nd4b
