@@ -105,16 +105,21 @@ __device__ __forceinline__ void sts2_if(bool pred, double* p, double x, double y
                ::"r"((unsigned)pred), "r"(smem_u32(p)), "d"(x), "d"(y) : "memory");
 }
 
+// x with its sign bit xor-ed by mask (0 or 0x80000000): sign flips without the FP64 pipe.
+__device__ __forceinline__ double flip(double x, unsigned mask) {
+  return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+}
+
 // ---- panel P: unblocked Householder on columns 8P..8P+7 (my column: 8P+g), rows >= 8P ----
 // xs: two 64-double buffers; the pivot column (rows above the pivot row zeroed) is published there by its quad and
 // read back by every lane with broadcast 16-byte loads (a shuffle broadcast of 16 doubles costs 32 SHFL per step).
 // The step is one dependent chain (dots -> |x|^2 -> reflector scalars -> update), so the scalar part is written for
 // depth: branch-free, 1/sqrt and 1/v0 refined from overlapping 20-bit estimates.
 template <int P, bool REREAD>
-__device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int lane, int g, int t, double& tau_q, double& sgn_q) {
+__device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int lane, int g, int t, double& tau_q, unsigned& sgn_q) {
   double inv_q = 0.0;
   tau_q = 0.0;
-  sgn_q = 1.0;
+  sgn_q = 0u;
   if (g == 0) {
 #pragma unroll
     for (int j = P; j < 8; j++) *reinterpret_cast<double2*>(xs + 8 * j + 2 * t) = make_double2(a[P][j][0], a[P][j][1]);
@@ -183,7 +188,7 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
       const bool piv = (g == kk);
       tau_q = piv ? (ok ? tau : 0.0) : tau_q;
       inv_q = piv ? (ok ? fma(e2, r1, r1) : 0.0) : inv_q;
-      sgn_q = piv ? ((ok && cn > 0.0) ? -1.0 : 1.0) : sgn_q;
+      sgn_q = piv ? ((ok ? ~(unsigned)__double2hiint(cn) : 0u) & 0x80000000u) : sgn_q;  // beta = -cn < 0: flip the row of R / column of Q
       const double beta = ok ? -cn : 0.0;
       a[P][P][0] = (piv && prow && !e0) ? beta : a[P][P][0];
       a[P][P][1] = (piv && prow && e0) ? beta : a[P][P][1];
@@ -258,29 +263,30 @@ __device__ __forceinline__ void qb_trailing(double (&a)[4][8][2], const double* 
 // R rows 8P..8P+7 (rows with beta < 0 negated, times post) for column block I.
 template <int P, int I>
 __device__ __forceinline__ void qb_store_r(const double (&a)[4][8][2], double* __restrict__ r_out, int g, int t,
-                                           double s0, double s1) {
+                                           unsigned s0, unsigned s1, double post) {
   const int row0 = 8 * P + 2 * t, col = 8 * I + g;
   double v0, v1;
   if (I < P) { v0 = 0.0; v1 = 0.0; }
-  else if (I == P) { v0 = (2 * t <= g) ? s0 * a[I][P][0] : 0.0; v1 = (2 * t + 1 <= g) ? s1 * a[I][P][1] : 0.0; }
-  else { v0 = s0 * a[I][P][0]; v1 = s1 * a[I][P][1]; }
+  else if (I == P) { v0 = (2 * t <= g) ? flip(a[I][P][0], s0) : 0.0; v1 = (2 * t + 1 <= g) ? flip(a[I][P][1], s1) : 0.0; }
+  else { v0 = flip(a[I][P][0], s0); v1 = flip(a[I][P][1], s1); }
+  if (post != 1.0) { v0 *= post; v1 *= post; }  // warp-uniform, extreme magnitudes only
   r_out[row0 * 32 + col] = v0;
   r_out[(row0 + 1) * 32 + col] = v1;
 }
 
 template <int P, bool REREAD>
 __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, double* ts,
-                                           double* __restrict__ r_out, int lane, int g, int t, double post, double& sgn_p,
+                                           double* __restrict__ r_out, int lane, int g, int t, double post, unsigned& sgn_p,
                                            long long& qb_tm) {
   double tau_q;
   qb_panel<P, REREAD>(a, vs + kXsOff, lane, g, t, tau_q, sgn_p);
   QB_MARK(2);
-  const double s0 = shfl(sgn_p, 4 * (2 * t)) * post, s1 = shfl(sgn_p, 4 * (2 * t + 1)) * post;
+  const unsigned s0 = __shfl_sync(kFull, sgn_p, 4 * (2 * t)), s1 = __shfl_sync(kFull, sgn_p, 4 * (2 * t + 1));
   // R: diagonal block and the zero blocks left of it; then the head of the panel becomes the clean unit-lower V
-  if (P > 0) qb_store_r<P, 0>(a, r_out, g, t, s0, s1);
-  if (P > 1) qb_store_r<P, 1>(a, r_out, g, t, s0, s1);
-  if (P > 2) qb_store_r<P, 2>(a, r_out, g, t, s0, s1);
-  qb_store_r<P, P>(a, r_out, g, t, s0, s1);
+  if (P > 0) qb_store_r<P, 0>(a, r_out, g, t, s0, s1, post);
+  if (P > 1) qb_store_r<P, 1>(a, r_out, g, t, s0, s1, post);
+  if (P > 2) qb_store_r<P, 2>(a, r_out, g, t, s0, s1, post);
+  qb_store_r<P, P>(a, r_out, g, t, s0, s1, post);
   a[P][P][0] = (2 * t > g) ? a[P][P][0] : ((2 * t == g) ? 1.0 : 0.0);
   a[P][P][1] = (2 * t + 1 > g) ? a[P][P][1] : ((2 * t + 1 == g) ? 1.0 : 0.0);
 #pragma unroll
@@ -296,9 +302,9 @@ __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, dou
   QB_MARK(4);
   if (P < 3) {
     qb_trailing<P, P>(a, vs, g, t, TT);
-    if (P < 1) qb_store_r<P, 1>(a, r_out, g, t, s0, s1);
-    if (P < 2) qb_store_r<P, 2>(a, r_out, g, t, s0, s1);
-    qb_store_r<P, 3>(a, r_out, g, t, s0, s1);
+    if (P < 1) qb_store_r<P, 1>(a, r_out, g, t, s0, s1, post);
+    if (P < 2) qb_store_r<P, 2>(a, r_out, g, t, s0, s1, post);
+    qb_store_r<P, 3>(a, r_out, g, t, s0, s1, post);
   }
   QB_MARK(5);
 }
@@ -386,7 +392,7 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   const double post = 1.0 / pre;
 
   double* r_out = R + m * 1024;
-  double sgn[4];
+  unsigned sgn[4];
   QB_MARK(0);
   qb_r_phase<0, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm);
   qb_r_phase<1, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm);
@@ -407,7 +413,7 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
 #pragma unroll
       for (int e = 0; e < 2; e++)
 #pragma unroll
-        for (int i = 0; i < 4; i++) vs[(8 * j + 2 * t + e) * 32 + 8 * i + g] = sgn[i] * a[i][j][e];
+        for (int i = 0; i < 4; i++) vs[(8 * j + 2 * t + e) * 32 + 8 * i + g] = flip(a[i][j][e], sgn[i]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) bulk_store(q_out, vs, 16384);
@@ -417,7 +423,7 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
 #pragma unroll
       for (int e = 0; e < 2; e++)
 #pragma unroll
-        for (int i = 0; i < 4; i++) q_out[(8 * j + 2 * t + e) * 32 + 8 * i + g] = sgn[i] * a[i][j][e];
+        for (int i = 0; i < 4; i++) q_out[(8 * j + 2 * t + e) * 32 + 8 * i + g] = flip(a[i][j][e], sgn[i]);
   }
   QB_MARK(7);
 }
