@@ -41,6 +41,18 @@ WORKLOADS = {
 }
 
 
+# FP64 roofline denominator: the DMMA.8x8x4 peak measured on this pool's B200 (profiles/r01_fp64_peak.json; the DFMA peak
+# is 36.83 — both instruction kinds share one pipe).  MEASURED_PEAKS.json holds no FP64 entry.
+FP64_PEAK_TFLOPS = 37.15
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the `ncu --set full` captures
+# summarised under profiles/ (file named per entry); None where no capture of the current kernel exists.
+NCU_TRAFFIC_BYTES = {
+    "c2": (1.577e9, "profiles/r01_ncu_c2_final.txt"),
+    "c4": (2.699e9, "profiles/r01_ncu_c4_blocked.txt"),
+}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -177,7 +189,22 @@ class DeviceCase:
             self.a = u(units, 64, 64)
             self.out = [torch.empty(units, 64, 64, **f64), torch.empty(units, 64, **f64), torch.empty(units, 64, 64, **f64)]
             self.sweeps = torch.zeros(4, dtype=torch.int32, device="cuda")
+            # per-matrix sweep counts of every launch are summed here: work per matrix is proportional to its sweeps
+            self.sweep_sum = torch.zeros(1, dtype=torch.int64, device="cuda")
+            self.launches = 0
+            if lib.nd4b_dev_svd_sweep_counter(dev, C.c_void_p(self.sweep_sum.data_ptr())):
+                raise RuntimeError(lib.nd4b_last_error().decode())
         torch.cuda.synchronize()
+
+    def mean_sweeps(self):
+        """Mean Jacobi sweeps per matrix over all launches so far (None for the other workloads)."""
+        if self.sweeps is None or not self.launches:
+            return None
+        return float(self.sweep_sum.item()) / (self.launches * self.units)
+
+    def close(self):
+        if self.sweeps is not None:
+            self.lib.nd4b_dev_svd_sweep_counter(self.dev, None)
 
     def step(self, stream):
         L, p, d = self.lib, (lambda t: C.c_void_p(t.data_ptr())), self.dev
@@ -193,6 +220,7 @@ class DeviceCase:
         else:
             rc = L.nd4b_dev_svd_jac1_f64(d, s, p(self.a), p(self.out[0]), p(self.out[1]), p(self.out[2]),
                                          self.units, 64, 64, p(self.sweeps), None, 0)
+            self.launches += 1
         if rc:
             raise RuntimeError("nd4b call failed: %s" % self.lib.nd4b_last_error().decode())
 
@@ -294,10 +322,12 @@ def run_ours(args):
     barrier()
     secs = max_over_ranks(secs, device="cuda")
     sweeps = int(case.sweeps[0].item()) if case.sweeps is not None else None
+    sweeps_mean = case.mean_sweeps()
     value = world * units * args.steps / secs
     launch_s = secs / args.steps
-    flop_unit = fpu * (sweeps if sweeps else 1)
+    flop_unit = fpu * (sweeps_mean if sweeps_mean else 1)  # Jacobi work is proportional to the sweeps each matrix needed
     achieved_gbs = bpu * units / launch_s / 1e9
+    case.close()
     del case
     torch.cuda.empty_cache()
 
@@ -306,7 +336,8 @@ def run_ours(args):
             sampler.stop()
         if rank == 0:
             emit({"workload": args.workload, "ms_per_launch": 1e3 * launch_s, "matrices_per_s": value,
-                  "gflops": value * flop_unit / 1e9, "hbm_gbs_algorithmic": achieved_gbs, "sweeps": sweeps})
+                  "gflops": value * flop_unit / 1e9, "hbm_gbs_algorithmic": achieved_gbs, "sweeps_max": sweeps,
+                  "sweeps_mean": sweeps_mean})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -348,14 +379,15 @@ def run_ours(args):
                     "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1"}[args.workload]},
             "gpu_launches": args.steps + int(e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[0],
+                         "traffic_source": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[1], "peak_source": peak_src,
                          "kernel": {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
-                                    "c4": "qr64x32_kernel", "c5": "svd64cb_kernel"}[args.workload],
+                                    "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel"}[args.workload],
                          "algorithmic_bytes_per_unit": bpu, "units_per_launch": units},
             "clocks": clocks,
         }
         if sweeps:
-            line["sweeps"] = sweeps
+            line["sweeps_max"], line["sweeps_mean"] = sweeps, sweeps_mean
         if args.fp64_probes:
             line["fp64_peaks_measured"] = fp64_peaks(lib, local)
         else:
@@ -376,10 +408,15 @@ def run_ours(args):
             n2 = 3 if name == "c5" else 10
             s2 = time_device(torch, c2, n2, 3)
             s2 = max_over_ranks(s2, device="cuda")
-            sw = int(c2.sweeps[0].item()) if c2.sweeps is not None else 1
+            sw = c2.mean_sweeps() or 1
+            gf = world * u2 * n2 / s2 * f2 * sw / 1e9
+            gbs = b2 * u2 * n2 / s2 / 1e9
             others[name] = {"workload": d2, "matrices_per_s": world * u2 * n2 / s2, "ms_per_launch": 1e3 * s2 / n2,
-                            "gflops": world * u2 * n2 / s2 * f2 * sw / 1e9, "hbm_gbs_algorithmic": b2 * u2 * n2 / s2 / 1e9,
-                            "sweeps": sw if name == "c5" else None}
+                            "gflops": gf, "hbm_gbs_algorithmic": gbs,
+                            "frac_of_hbm_peak": gbs / world / hbm_peak, "frac_of_fp64_peak": gf / world / 1e3 / FP64_PEAK_TFLOPS,
+                            "sweeps_mean": sw if name == "c5" else None,
+                            "sweeps_max": int(c2.sweeps[0].item()) if name == "c5" else None}
+            c2.close()
             del c2
             torch.cuda.empty_cache()
         if rank == 0:

@@ -136,6 +136,11 @@ int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, 
 size_t nd4b_dev_qr_workspace(int64_t batch, int rows, int cols);
 size_t nd4b_dev_svd_workspace(int64_t batch, int rows, int cols);
 
+/* Diagnostic for the flop accounting of the benchmark: from now on every SVD launch on `device` adds the sweep count of
+ * each matrix to *counter (device uint64, caller-initialised; NULL switches it off).  The Jacobi sweep count is data
+ * dependent (C5: 10.06 on average, 12 at most), and work per matrix is proportional to it. */
+int nd4b_dev_svd_sweep_counter(int device, unsigned long long* counter);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 
 /* Times one launch of an FP64 pipe probe on `device` (which: 0 = DFMA vector pipe, 16 chains x 2 flop x iters

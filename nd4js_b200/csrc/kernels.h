@@ -43,6 +43,9 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
                             int64_t batch, int rows, int cols, int* sweeps, int* fail,
                             double* work, size_t work_bytes);
 
+// diagnostic: per-matrix sweep counts of the following SVD launches on `device` are added to *counter (device memory)
+void set_svd_sweep_counter(int device, unsigned long long* counter);
+
 // fp64 peak probes (tools/ and bench use them to measure the FP64 roofline denominators)
 cudaError_t launch_probe_dfma(cudaStream_t s, double* out, int iters, int blocks, int threads);
 cudaError_t launch_probe_dmma(cudaStream_t s, double* out, int iters, int blocks, int threads);

@@ -864,6 +864,13 @@ int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, 
                                                  workspace, workspace_bytes), ctx);
 }
 
+int nd4b_dev_svd_sweep_counter(int device, unsigned long long* counter) {
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  nd4b::set_svd_sweep_counter(device, counter);
+  return ND4B_OK;
+}
+
 // FP64 pipe probes (not part of the nd.la surface; used by tools/fp64_peak.py and bench.py).
 int nd4b_probe_fp64(int device, int which, int iters, int blocks, int threads, float* ms_out) {
   Context* ctx; int sms;

@@ -192,7 +192,7 @@ __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* s
 
 __global__ void __launch_bounds__(kSvd64Threads, 3)
 svd64_smem_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
-             int64_t batch, int* sweeps_out, int* fail_out) {
+             int64_t batch, int* sweeps_out, int* fail_out, unsigned long long* sweep_sum) {
   constexpr int N = 64, LD = kSvd64LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Gs = reinterpret_cast<double*>(smem_raw);
@@ -271,6 +271,7 @@ svd64_smem_kernel(const double* __restrict__ A, double* __restrict__ U, double* 
   }
   if (tid == 0) {
     if (sweeps_out) atomicMax(sweeps_out, sweeps);
+    if (sweep_sum) atomicAdd(sweep_sum, (unsigned long long)sweeps);
     if (!converged && fail_out) atomicExch(fail_out, 1);
   }
 
@@ -330,23 +331,46 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
   r.alpha = 0.0; r.beta = 0.0;
   na2 = na; nb2 = nb; Dp2 = Dp; Dpi2 = Dpi; Dq2 = Dq; Dqi2 = Dqi;
   const double d = dhat * Dp * Dq;
-  if (have && d * d > tol2 * na * nb) {
+  // The set-up runs warp-uniformly (if any pair of the warp rotates, every lane executes it and pairs below the threshold
+  // discard the result with selects): a divergent branch here costs a reconvergence barrier in every step.
+  const bool rot = have && d * d > tol2 * na * nb;
+  if (__any_sync(kFull, rot)) {
     double num = nb - na, den = 2.0 * d;
     if (fabs(num) + fabs(den) < 1e-140) { num *= 0x1p600; den *= 0x1p600; }  // only the ratio matters; keep num^2+den^2 normal
-    const double rh = rsqrt_nr(fma(num, num, den * den));
-    const double c2 = fabs(num) * rh, s2 = fabs(den) * rh;   // cos 2theta, |sin 2theta|
-    const double hc = fma(0.5, c2, 0.5);                     // c^2
-    const double rc = rsqrt_nr(hc);                          // 1/c
+    // Critical path of a step: t = tan(theta) = sin(2 theta) / (1 + cos(2 theta)).  1/sqrt(S) by one cubic step from the
+    // hardware seed y0 (2^-22 -> ~2^-66); the reciprocal of w = 1 + cos(2 theta) in [1,2] by two Newton steps from a seed
+    // taken at the approximate w, so that the two special-function latencies overlap.  c and 1/c (needed only for the
+    // scales and norms of the NEXT step) follow off the critical path.
+    const double S = fma(num, num, den * den);
+    const double an = fabs(num), ad = fabs(den);
+    double y0, r0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(S));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(fma(an, y0, 1.0)));
+    const double e = fma(-S * y0, y0, 1.0);
+    const double rh = fma(y0 * e, fma(0.375, e, 0.5), y0);
+    const double c2 = an * rh, s2 = ad * rh;                 // cos 2theta, |sin 2theta|
+    const double w = 1.0 + c2;                               // 2 c^2
+    const double r1 = fma(fma(-w, r0, 1.0), r0, r0);
+    const double rw = fma(fma(-w, r1, 1.0), r1, r1);         // 1 / w
+    double t = s2 * rw;
+    if ((num < 0.0) != (den < 0.0)) t = -t;
+    const double hc = 0.5 * w;                               // c^2
+    double rc;                                               // 1/c, one cubic step (hc in [0.5, 1])
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(hc));
+    {
+      const double e1 = fma(-hc * rc, rc, 1.0);
+      rc = fma(rc * e1, fma(0.375, e1, 0.5), rc);
+    }
     const double c = hc * rc;
-    double sn = 0.5 * s2 * rc;                               // |s|
-    if ((num < 0.0) != (den < 0.0)) sn = -sn;
-    const double t = sn * rc;
-    r.alpha = t * Dq * Dpi;
-    r.beta = t * Dp * Dqi;
-    Dp2 = c * Dp; Dq2 = c * Dq; Dpi2 = rc * Dpi; Dqi2 = rc * Dqi;
+    const double sn = t * c;
     const double cc = hc, ss = sn * sn, csd = 2.0 * c * sn * d;
-    na2 = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);         // |c p - s q|^2
-    nb2 = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);          // |s p + c q|^2
+    const double na_r = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);  // |c p - s q|^2
+    const double nb_r = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);   // |s p + c q|^2
+    r.alpha = rot ? t * Dq * Dpi : 0.0;
+    r.beta = rot ? t * Dp * Dqi : 0.0;
+    Dp2 = rot ? c * Dp : Dp; Dq2 = rot ? c * Dq : Dq; Dpi2 = rot ? rc * Dpi : Dpi; Dqi2 = rot ? rc * Dqi : Dqi;
+    na2 = rot ? na_r : na;
+    nb2 = rot ? nb_r : nb;
     rotated = 1;
   }
   return r;
@@ -437,7 +461,7 @@ constexpr size_t kSvd64CbSmem = sizeof(double) * (2 * 64 * kSvd64LD + 64 + 2 * 4
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
-               int64_t batch, int* sweeps_out, int* fail_out) {
+               int64_t batch, int* sweeps_out, int* fail_out, unsigned long long* sweep_sum) {
   constexpr int N = 64, LD = kSvd64LD, XS = 136;       // XS: doubles per exchange record (4*32 column values + norm, D, 1/D)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Gs = reinterpret_cast<double*>(smem_raw);
@@ -552,6 +576,7 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
   }
   if (tid == 0) {
     if (sweeps_out) atomicMax(sweeps_out, sweeps);
+    if (sweep_sum) atomicAdd(sweep_sum, (unsigned long long)sweeps);
     if (!converged && fail_out) atomicExch(fail_out, 1);
   }
 #pragma unroll
@@ -578,7 +603,8 @@ __host__ __device__ inline size_t svd_gen_scratch_doubles(int rows, int cols) {
 
 __global__ void __launch_bounds__(kSvdGenThreads)
 svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
-                   int64_t batch, int rows, int cols, int* sweeps_out, int* fail_out, double* __restrict__ work) {
+                   int64_t batch, int rows, int cols, int* sweeps_out, int* fail_out, double* __restrict__ work,
+                   unsigned long long* sweep_sum) {
   const int64_t m = blockIdx.x;
   if (m >= batch) return;
   const bool wide = rows < cols;
@@ -656,6 +682,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   }
   if (tid == 0) {
     if (sweeps_out) atomicMax(sweeps_out, sweeps);
+    if (sweep_sum) atomicAdd(sweep_sum, (unsigned long long)sweeps);
     if (!converged && fail_out) atomicExch(fail_out, 1);
   }
 
@@ -715,6 +742,12 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   for (int l = tid; l < n; l += kSvdGenThreads) SV[m * n + l] = zero_flag[perm[l]] ? 0.0 : sig[perm[l]] * post;
 }
 
+// Diagnostic: device counter that every following SVD launch on `device` adds its per-matrix sweep counts to (nullptr: off).
+static unsigned long long* g_sweep_sum[64] = {nullptr};
+void set_svd_sweep_counter(int device, unsigned long long* counter) {
+  if (device >= 0 && device < 64) g_sweep_sum[device] = counter;
+}
+
 size_t svd_workspace_bytes(int64_t batch, int rows, int cols) {
   if (rows == 64 && cols == 64) return 0;
   return sizeof(double) * (size_t)batch * svd_gen_scratch_doubles(rows, cols);
@@ -725,10 +758,11 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
                             double* work, size_t work_bytes) {
   if (batch <= 0) return cudaSuccess;
   if (batch > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  unsigned long long* ssum = (dev >= 0 && dev < 64) ? g_sweep_sum[dev] : nullptr;
   if (rows == 64 && cols == 64) {
     static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
       cudaError_t e = cudaFuncSetAttribute(svd64cb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64CbSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64Smem);
@@ -740,13 +774,13 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
       const char* ev = getenv("ND4B_SVD_VARIANT");
       variant = ev ? atoi(ev) : 0;  // 1 = the shared-memory baseline kernel (kept for A/B profiling)
     }
-    if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail);
-    else svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail);
+    if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail, ssum);
+    else svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail, ssum);
     return cudaGetLastError();
   }
   const size_t need = svd_workspace_bytes(batch, rows, cols);
   if (work == nullptr || work_bytes < need) return cudaErrorInvalidValue;
-  svd_generic_kernel<<<(unsigned)batch, kSvdGenThreads, 0, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, work);
+  svd_generic_kernel<<<(unsigned)batch, kSvdGenThreads, 0, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, work, ssum);
   return cudaGetLastError();
 }
 
