@@ -83,6 +83,16 @@ int nd4b_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
                     const double* B, const int32_t* b_shape, int b_ndim,
                     double* C, const int32_t* c_shape, int c_ndim);
 
+/* ---- nd.la.matmul(...matrices) — src/la/matmul.js:150-236 --------------------------------------- */
+
+/* Executes a matrix-chain product with all intermediates resident in HBM.  The caller (the JS shim / la.py) keeps the
+ * reference's ordering DP (:159-235) and passes the parenthesisation as a postfix plan: an entry >= 0 pushes operand
+ * mats[entry] (shape shapes[entry], ndims[entry] dims), -1 replaces the two topmost items a, b (b on top) by matmul2(a, b)
+ * with the broadcasting and error texts of nd4b_matmul_f64.  E.g. a.(b.c) = {0, 1, 2, -1, -1}.  c_shape must be the shape
+ * of the final product. */
+int nd4b_matmul_plan_f64(int n, const double* const* mats, const int32_t* const* shapes, const int* ndims,
+                         const int32_t* plan, int plan_len, double* C, const int32_t* c_shape, int c_ndim);
+
 /* ---- nd.la.cholesky_decomp — src/la/cholesky.js:50-72, _cholesky_decomp :27-47 --------------- */
 
 /* Reads only the lower triangle of every S; L's strict upper triangle is +0.  On ND4B_E_SINGULAR
@@ -95,6 +105,15 @@ int nd4b_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t*
 /* Q[batch,rows,min(rows,cols)], R[batch,min(rows,cols),cols]; R exactly upper triangular with
  * diag(R) >= 0 (the reference's Givens QR leaves arbitrary signs on diag(R): compare sign-normalised). */
 int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols);
+
+/* ---- nd.la._qr_decomp_inplace — src/la/qr.js:147-183 (the QR of the trust-region least-squares solvers,
+ *      src/opt/_trust_region_solver_tls.js:1126): factorise A and apply Q^T to right-hand sides without forming Q -------- */
+
+/* A[batch,M,N], Y[batch,M,L] -> R[batch,M,N] (upper trapezoidal, exact zeros below the diagonal, diag >= 0) and
+ * QtY[batch,M,L] = Q^T Y with the full M x M orthogonal Q of A = Q R.  The reference works in place on A and Y; here the
+ * inputs are read-only and the results go to R and QtY (which may not alias the inputs).  Rows min(M,N).. of QtY are
+ * coordinates in an orthonormal basis of range(A)'s complement: only their norms are basis independent. */
+int nd4b_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY, int64_t batch, int M, int N, int L);
 
 /* ---- nd.la.svd_jac_1sided — contract of the svd_jac_* family, src/la/svd_jac_2sided.js:30-144,
  *      ordering/sign rules src/la/_svd_jac_utils.js:123-188, shapes src/help.js:2321-2337 ------- */
@@ -128,6 +147,8 @@ int nd4b_dev_cholesky_f64(int device, void* stream, const double* S, double* L,
                           int64_t batch, int n, long long* info);
 int nd4b_dev_qr_f64(int device, void* stream, const double* A, double* Q, double* R,
                     int64_t batch, int rows, int cols, double* workspace, size_t workspace_bytes);
+int nd4b_dev_qr_inplace_f64(int device, void* stream, const double* A, const double* Y, double* R, double* QtY,
+                            int64_t batch, int M, int N, int L);
 /* sweeps (device int32, may be NULL): atomicMax of sweeps used.  workspace as reported below. */
 int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, double* sv, double* V,
                           int64_t batch, int rows, int cols, int* sweeps,

@@ -74,6 +74,30 @@ napi_value Matmul(napi_env env, napi_callback_info info) {
   return undefined(env);
 }
 
+// matmulPlan(mats:Array<Float64Array>, shapes:Array<Int32Array>, plan:Int32Array, c:Float64Array, cShape:Int32Array)
+// — the chain product of nd.la.matmul with its intermediates kept in HBM (nd4b_matmul_plan_f64)
+napi_value MatmulPlan(napi_env env, napi_callback_info info) {
+  size_t argc = 5; napi_value v[5];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  uint32_t n = 0, ns = 0;
+  I32 plan, cs; F64 c;
+  if (argc < 5 || napi_get_array_length(env, v[0], &n) != napi_ok || napi_get_array_length(env, v[1], &ns) != napi_ok || n != ns ||
+      n < 1 || n > 64 || !get_i32(env, v[2], &plan) || !get_f64(env, v[3], &c) || !get_i32(env, v[4], &cs)) {
+    napi_throw_error(env, nullptr, "nd4b: matmulPlan(mats, shapes, plan, c, cShape)"); return nullptr;
+  }
+  const double* mats[64]; const int32_t* shapes[64]; int ndims[64];
+  for (uint32_t i = 0; i < n; i++) {
+    napi_value m, s; F64 mf; I32 sf;
+    if (napi_get_element(env, v[0], i, &m) != napi_ok || napi_get_element(env, v[1], i, &s) != napi_ok ||
+        !get_f64(env, m, &mf) || !get_i32(env, s, &sf)) return nullptr;
+    if ((int64_t)mf.n != prod(sf)) { napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr; }
+    mats[i] = mf.p; shapes[i] = sf.p; ndims[i] = (int)sf.n;
+  }
+  if ((int64_t)c.n != prod(cs)) { napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr; }
+  if (nd4b_matmul_plan_f64((int)n, mats, shapes, ndims, plan.p, (int)plan.n, c.p, cs.p, (int)cs.n)) return fail(env);
+  return undefined(env);
+}
+
 // cholesky(S:Float64Array, L:Float64Array, batch, n)
 napi_value Cholesky(napi_env env, napi_callback_info info) {
   size_t argc = 4; napi_value v[4];
@@ -98,6 +122,20 @@ napi_value Qr(napi_env env, napi_callback_info info) {
     napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
   }
   if (nd4b_qr_f64(a.p, q.p, r.p, batch, (int)rows, (int)cols)) return fail(env);
+  return undefined(env);
+}
+
+// qrInplace(A, Y, R, QtY, batch, M, N, L)
+napi_value QrInplace(napi_env env, napi_callback_info info) {
+  size_t argc = 8; napi_value v[8];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 a, y, r, q; int64_t batch, m, n, l;
+  if (argc < 8 || !get_f64(env, v[0], &a) || !get_f64(env, v[1], &y) || !get_f64(env, v[2], &r) || !get_f64(env, v[3], &q) ||
+      !get_int(env, v[4], &batch) || !get_int(env, v[5], &m) || !get_int(env, v[6], &n) || !get_int(env, v[7], &l)) return nullptr;
+  if ((int64_t)a.n != batch * m * n || r.n != a.n || (int64_t)y.n != batch * m * l || q.n != y.n) {
+    napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
+  }
+  if (nd4b_qr_inplace_f64(a.p, y.p, r.p, q.p, batch, (int)m, (int)n, (int)l)) return fail(env);
   return undefined(env);
 }
 
@@ -178,8 +216,10 @@ napi_value RegisterAll(napi_env env, napi_value exports) {
   const napi_property_descriptor props[] = {
       {"matmulShape", nullptr, MatmulShape, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"matmul", nullptr, Matmul, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"matmulPlan", nullptr, MatmulPlan, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"cholesky", nullptr, Cholesky, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"qr", nullptr, Qr, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"qrInplace", nullptr, QrInplace, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"triSolve", nullptr, TriSolve, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"svdJac1", nullptr, SvdJac1, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"pinnedFloat64Array", nullptr, PinnedFloat64Array, nullptr, nullptr, nullptr, napi_default, nullptr},

@@ -35,6 +35,8 @@ napi_status napi_get_cb_info(napi_env env, napi_callback_info cbinfo, size_t* ar
                              napi_value* this_arg, void** data);
 napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type, size_t* length,
                                      void** data, napi_value* arraybuffer, size_t* byte_offset);
+napi_status napi_get_array_length(napi_env env, napi_value value, uint32_t* result);
+napi_status napi_get_element(napi_env env, napi_value object, uint32_t index, napi_value* result);
 napi_status napi_get_value_int32(napi_env env, napi_value value, int32_t* result);
 napi_status napi_get_value_int64(napi_env env, napi_value value, int64_t* result);
 napi_status napi_get_value_double(napi_env env, napi_value value, double* result);

@@ -640,6 +640,82 @@ int nd4b_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
   return run_pipeline(ctx, batch, ins, outs, 0, launch);
 }
 
+// ---- matmul chain: nd.la.matmul(...matrices), src/la/matmul.js:150-236 ---------------------------
+// The parenthesisation (the reference's DP over broadcast-aware flop counts, :159-235) stays with the caller and arrives
+// as a postfix plan; here the plan is executed with every intermediate product kept in HBM: operands go up once, one
+// result comes down.  Runs on the first device of the context (a chain is a dependent sequence, not a batch to shard).
+int nd4b_matmul_plan_f64(int n, const double* const* mats, const int32_t* const* shapes, const int* ndims,
+                         const int32_t* plan, int plan_len, double* C, const int32_t* c_shape, int c_ndim) {
+  if (n < 1 || !mats || !shapes || !ndims || !plan || plan_len < 1 || !C || !c_shape) return fail(ND4B_E_ARG, "matmul_plan: bad argument");
+  for (int i = 0; i < n; i++) {
+    if (!mats[i] || !shapes[i]) return fail(ND4B_E_ARG, "matmul_plan: null operand %d", i);
+    if (ndims[i] < 2) return fail(i == 0 ? ND4B_E_A_NDIM : ND4B_E_B_NDIM, "%s", ref_message(i == 0 ? ND4B_E_A_NDIM : ND4B_E_B_NDIM));
+    if (ndims[i] > ND4B_MAX_NDIM) return fail(ND4B_E_ARG, "matmul: ndim > %d", ND4B_MAX_NDIM);
+    for (int d = 0; d < ndims[i]; d++) if (shapes[i][d] < 1) return fail(ND4B_E_ARG, "Invalid shape: dims must be >= 1.");
+  }
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  Device& dev = ctx->devs[0];
+  CU(cudaSetDevice(dev.id));
+  cudaStream_t st = dev.slots[0].stream;
+
+  struct Item { double* p; std::vector<int32_t> shape; };
+  std::vector<Item> stack;
+  std::vector<void*> owned;
+  auto cleanup = [&](int rc) {
+    cudaStreamSynchronize(st);
+    for (void* q : owned) cudaFree(q);
+    return rc;
+  };
+  auto elems = [](const std::vector<int32_t>& shp) { int64_t e = 1; for (int32_t v : shp) e *= v; return e; };
+  for (int t = 0; t < plan_len; t++) {
+    const int32_t op = plan[t];
+    if (op >= 0) {
+      if (op >= n) return cleanup(fail(ND4B_E_ARG, "matmul_plan: operand index %d out of range", op));
+      Item it{nullptr, std::vector<int32_t>(shapes[op], shapes[op] + ndims[op])};
+      const size_t bytes = (size_t)elems(it.shape) * 8;
+      if (cudaMalloc(&it.p, bytes) != cudaSuccess) return cleanup(fail(ND4B_E_CUDA, "matmul_plan: out of device memory"));
+      owned.push_back(it.p);
+      if (cudaMemcpyAsync(it.p, mats[op], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return cleanup(fail(ND4B_E_CUDA, "matmul_plan: H2D copy failed"));
+      ctx->h2d += bytes;
+      stack.push_back(std::move(it));
+      continue;
+    }
+    if (stack.size() < 2) return cleanup(fail(ND4B_E_ARG, "matmul_plan: malformed plan"));
+    Item b = std::move(stack.back()); stack.pop_back();
+    Item a = std::move(stack.back()); stack.pop_back();
+    const int an = (int)a.shape.size(), bn = (int)b.shape.size();
+    Item c{nullptr, std::vector<int32_t>(std::max(an, bn))};
+    int cn = 0;
+    if (int rc = nd4b_matmul_shape(a.shape.data(), an, b.shape.data(), bn, c.shape.data(), &cn)) return cleanup(rc);
+    BatchMap map;
+    bool a_full, b_full;
+    int64_t a_count, b_count;
+    if (int rc = build_batch_map(a.shape.data(), an, b.shape.data(), bn, c.shape.data(), cn, &map, &a_full, &b_full, &a_count, &b_count)) return cleanup(rc);
+    const int I = a.shape[an - 2], K = a.shape[an - 1], J = b.shape[bn - 1];
+    int64_t batch = 1;
+    for (int d = 0; d < cn - 2; d++) batch *= c.shape[d];
+    map.base = 0;
+    map.a_lin = a_full ? (int64_t)I * K : (a_count == 1 ? 0 : -1);
+    map.b_lin = b_full ? (int64_t)K * J : (b_count == 1 ? 0 : -1);
+    if (cudaMalloc(&c.p, (size_t)elems(c.shape) * 8) != cudaSuccess) return cleanup(fail(ND4B_E_CUDA, "matmul_plan: out of device memory"));
+    owned.push_back(c.p);
+    if (int rc = check_cuda_launch(nd4b::launch_matmul(st, a.p, b.p, c.p, batch, I, K, J, map, dev.sm_count), ctx)) return cleanup(rc);
+    stack.push_back(std::move(c));
+  }
+  if (stack.size() != 1) return cleanup(fail(ND4B_E_ARG, "matmul_plan: malformed plan"));
+  const Item& r = stack.back();
+  if ((int)r.shape.size() != c_ndim) return cleanup(fail(ND4B_E_SHAPE, "matmul: result ndim %d, expected %d", c_ndim, (int)r.shape.size()));
+  for (int d = 0; d < c_ndim; d++)
+    if (r.shape[d] != c_shape[d]) return cleanup(fail(ND4B_E_SHAPE, "matmul: result shape mismatch at dim %d", d));
+  const size_t bytes = (size_t)elems(r.shape) * 8;
+  if (cudaMemcpyAsync(C, r.p, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return cleanup(fail(ND4B_E_CUDA, "matmul_plan: D2H copy failed"));
+  ctx->d2h += bytes;
+  return cleanup(ND4B_OK);
+}
+
 // ---- cholesky -----------------------------------------------------------------------------------
 
 int nd4b_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t* first_bad) {
@@ -691,6 +767,20 @@ int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, 
   };
   return run_pipeline(ctx, batch, {{A, nullptr, (int64_t)rows * cols}},
                       {{nullptr, Q, (int64_t)rows * L}, {nullptr, R, (int64_t)L * cols}}, work_unit, launch);
+}
+
+int nd4b_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY, int64_t batch, int M, int N, int L) {
+  if (!A || !Y || !R || !QtY) return fail(ND4B_E_ARG, "qr_inplace: null pointer");
+  if (batch < 1 || M < 1 || N < 1 || L < 1) return fail(ND4B_E_ARG, "qr_inplace: batch, M, N and L must be >= 1");
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  auto launch = [&](const ChunkArgs& a) -> int {
+    return check_cuda_launch(nd4b::launch_qr_inplace(a.stream, a.in[0], a.in[1], a.out[0], a.out[1], a.count, M, N, L), ctx);
+  };
+  return run_pipeline(ctx, batch, {{A, nullptr, (int64_t)M * N}, {Y, nullptr, (int64_t)M * L}},
+                      {{nullptr, R, (int64_t)M * N}, {nullptr, QtY, (int64_t)M * L}}, 0, launch);
 }
 
 // ---- svd ----------------------------------------------------------------------------------------
@@ -853,6 +943,14 @@ int nd4b_dev_qr_f64(int device, void* stream, const double* A, double* Q, double
   Context* ctx; int sms;
   if (int rc = dev_enter(device, &ctx, &sms)) return rc;
   return check_cuda_launch(nd4b::launch_qr((cudaStream_t)stream, A, Q, R, batch, rows, cols, workspace, workspace_bytes), ctx);
+}
+
+int nd4b_dev_qr_inplace_f64(int device, void* stream, const double* A, const double* Y, double* R, double* QtY,
+                            int64_t batch, int M, int N, int L) {
+  if (!A || !Y || !R || !QtY || batch < 1 || M < 1 || N < 1 || L < 1) return fail(ND4B_E_ARG, "dev_qr_inplace: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  return check_cuda_launch(nd4b::launch_qr_inplace((cudaStream_t)stream, A, Y, R, QtY, batch, M, N, L), ctx);
 }
 
 int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, double* sv, double* V,

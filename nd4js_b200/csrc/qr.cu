@@ -349,6 +349,87 @@ qr_generic_kernel(const double* __restrict__ A, double* __restrict__ Q, double* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// _qr_decomp_inplace (nd4js src/la/qr.js:147-183): A[M,N] -> R (same shape, zero below the diagonal), Y[M,L] -> Q^T Y,
+// Q never formed.  One CTA per matrix working directly in the two output buffers (L2-resident); the reflectors are
+// applied to the trailing columns of A and to all columns of Y alike (one warp per column).  Same sign convention as the
+// other QR kernels: diag(R) >= 0 (the reference's Givens sequence leaves arbitrary signs; rows of R and of Q^T Y flip together).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kQrGenThreads)
+qr_inplace_kernel(const double* __restrict__ A, const double* __restrict__ Y, double* __restrict__ R, double* __restrict__ QtY,
+                  int64_t batch, int M, int N, int L) {
+  const int64_t m = blockIdx.x;
+  if (m >= batch) return;
+  const int64_t mn = (int64_t)M * N, ml = (int64_t)M * L;
+  const double* a_in = A + m * mn;
+  const double* y_in = Y + m * ml;
+  double* W = R + m * mn;
+  double* Z = QtY + m * ml;
+  __shared__ double red[kQrGenThreads / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kQrGenThreads / 32;
+
+  double amax = 0.0;
+  for (int64_t e = tid; e < mn; e += kQrGenThreads) { const double x = a_in[e]; W[e] = x; amax = fmax(amax, fabs(x)); }
+  for (int64_t e = tid; e < ml; e += kQrGenThreads) Z[e] = y_in[e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(kFull, amax, o));
+  if (lane == 0) red[warp] = amax;
+  __syncthreads();
+  amax = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) amax = fmax(amax, red[w]);
+  const double pre = pow2_prescale(amax), post = 1.0 / pre;
+  __syncthreads();
+  if (pre != 1.0) {
+    for (int64_t e = tid; e < mn; e += kQrGenThreads) W[e] *= pre;
+    __syncthreads();
+  }
+
+  const int K = M < N ? M : N;
+  for (int k = 0; k < K; k++) {
+    double part = 0.0;
+    for (int i = k + 1 + tid; i < M; i += kQrGenThreads) {
+      const double x = W[(int64_t)i * N + k];
+      part = fma(x, x, part);
+    }
+    const double sigma = block_sum(part, red);
+    const double x0 = W[(int64_t)k * N + k];
+    const Reflector h = make_reflector(x0, sigma);
+    __syncthreads();  // everyone has read x0
+    for (int i = k + 1 + tid; i < M; i += kQrGenThreads) W[(int64_t)i * N + k] *= h.inv_v0;
+    if (tid == 0) W[(int64_t)k * N + k] = h.beta;
+    __syncthreads();
+    // columns k+1..N-1 of A, then the L columns of Y: one warp per column
+    const int ncol = (N - 1 - k) + L;
+    for (int jj = warp; jj < ncol; jj += NW) {
+      const bool in_a = jj < N - 1 - k;
+      double* col = in_a ? W + (k + 1 + jj) : Z + (jj - (N - 1 - k));
+      const int ld = in_a ? N : L;
+      double w = (lane == 0) ? col[(int64_t)k * ld] : 0.0;  // v_k = 1
+      for (int i = k + 1 + lane; i < M; i += 32) w = fma(W[(int64_t)i * N + k], col[(int64_t)i * ld], w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
+      const double f = h.tau * w;
+      if (lane == 0) col[(int64_t)k * ld] -= f;
+      for (int i = k + 1 + lane; i < M; i += 32) col[(int64_t)i * ld] = fma(-f, W[(int64_t)i * N + k], col[(int64_t)i * ld]);
+    }
+    __syncthreads();
+  }
+  for (int64_t e = tid; e < mn; e += kQrGenThreads) {
+    const int i = (int)(e / N), j = (int)(e % N);
+    W[e] = (j >= i) ? W[e] * post : 0.0;
+  }
+}
+
+cudaError_t launch_qr_inplace(cudaStream_t s, const double* A, const double* Y, double* R, double* QtY,
+                              int64_t batch, int M, int N, int L) {
+  if (batch <= 0) return cudaSuccess;
+  if (batch > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  qr_inplace_kernel<<<(unsigned)batch, kQrGenThreads, 0, s>>>(A, Y, R, QtY, batch, M, N, L);
+  return cudaGetLastError();
+}
+
 size_t qr_workspace_bytes(int64_t batch, int rows, int cols) {
   if (rows == 64 && cols == 32) return 0;
   const int L = rows < cols ? rows : cols;

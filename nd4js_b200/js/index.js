@@ -57,17 +57,25 @@ function matmul(...matrices) {
       if (bestShape === undefined) throw new Error('Integer overflow (too many FLOPs).');
       op[i][i + len - 1] = [best, bestShape];
     }
+  // postfix plan of the optimal parenthesisation: i pushes operand i, -1 multiplies the two topmost items; the products
+  // then run with every intermediate kept in HBM (nd4b_matmul_plan_f64) instead of one host round trip per matmul2
+  const plan = [];
   const product = (from, to) => {
-    if (from === to) return matrices[from];
+    if (from === to) { plan.push(from); return; }
     let best = Infinity, idx;
     for (let i = from; i < to; i++) {
       const [lf, ls] = op[from][i], [rf, rs] = op[i + 1][to];
       let [f] = nOps(ls, rs); f += lf + rf;
       if (f < best) { best = f; idx = i; }
     }
-    return matmul2(product(from, idx), product(idx + 1, to));
+    product(from, idx); product(idx + 1, to); plan.push(-1);
   };
-  return product(0, n - 1);
+  product(0, n - 1);
+  for (const [i, m] of matrices.entries())
+    if (m.ndim < 2) throw new Error(i === 0 ? 'A must be at least 2D.' : 'B must be at least 2D.');
+  const shape = Int32Array.from(op[0][n - 1][1]), c = new Float64Array(shape.reduce((x, y) => x * y, 1));
+  addon.matmulPlan(matrices.map(m => f64(m, 'matmul')), matrices.map(m => Int32Array.from(m.shape)), Int32Array.from(plan), c, shape);
+  return new NDArray(shape, c);
 }
 
 function cholesky_decomp(S) {
@@ -88,6 +96,17 @@ function qr_decomp(A) {
   const Q = new Float64Array(batch * N * L), R = new Float64Array(batch * L * M);
   addon.qr(a, Q, R, batch, N, M);
   return [new NDArray(qShape, Q), new NDArray(rShape, R)];
+}
+
+// _qr_decomp_inplace(M,N,L, A,A_off, Y,Y_off) (qr.js:147-183): same in-place contract on flat arrays; A becomes R, Y becomes Q^T Y.
+function _qr_decomp_inplace(M, N, L, A, A_off, Y, Y_off) {
+  for (const x of [M, N, L, A_off, Y_off]) if (x % 1 !== 0 || !(0 <= x)) throw new Error('Assertion failed.');
+  if (!(M * N <= A.length - A_off) || !(M * L <= Y.length - Y_off)) throw new Error('Assertion failed.');
+  if (M === 0 || N === 0 || L === 0) return;
+  const a = Float64Array.from(A.subarray(A_off, A_off + M * N)), y = Float64Array.from(Y.subarray(Y_off, Y_off + M * L));
+  const R = new Float64Array(M * N), QtY = new Float64Array(M * L);
+  addon.qrInplace(a, y, R, QtY, 1, M, N, L);
+  A.set(R, A_off); Y.set(QtY, Y_off);
 }
 
 function svd_jac_1sided(A) {
@@ -119,6 +138,6 @@ const tril_solve = (L, Y) => triSolve(0, L, Y, 'tril_solve(L,Y): L.ndim must be 
 const triu_solve = (U, Y) => triSolve(1, U, Y, 'triu_solve(U,Y): U.ndim must be at least 2.', 'triu_solve(U,Y): Y.ndim must be at least 2.');
 const cholesky_solve = (L, y) => triSolve(2, L, y, 'L must be at least 2D.', 'y must be at least 2D.');
 
-module.exports = {matmul2, matmul, cholesky_decomp, qr_decomp, svd_jac_1sided, tril_solve, triu_solve, cholesky_solve,
+module.exports = {matmul2, matmul, cholesky_decomp, qr_decomp, _qr_decomp_inplace, svd_jac_1sided, tril_solve, triu_solve, cholesky_solve,
                   init: d => addon.init(Int32Array.from(d || [])), stats: addon.stats,
                   pinnedFloat64Array: addon.pinnedFloat64Array};

@@ -56,15 +56,10 @@ def matmul2(a, b):
     return NDArray(c_s, c)
 
 
-def matmul(*matrices):
-    """Matrix-chain product; the flop-optimal parenthesisation is found on the host exactly as in
-    matmul.js:159-235 (broadcast-aware flop counts), the leaves are matmul2 calls on the GPU."""
-    ms = [asarray(m) for m in matrices]
-    if len(ms) == 1:
-        return ms[0]
-    if len(ms) == 2:
-        return matmul2(*ms)
-
+def _chain_plan(shapes):
+    """The parenthesisation of matmul.js:159-235 for operands of the given shapes (broadcast-aware flop counts, ties broken
+    like the reference: first minimum wins), as a postfix plan: i >= 0 pushes operand i, -1 multiplies the two topmost
+    items.  Returns (plan, result_shape).  Host logic only."""
     def n_ops(sa, sb):
         i, k = sa[-2], sa[-1]
         j = sb[-1]
@@ -84,10 +79,10 @@ def matmul(*matrices):
                     raise ValueError("Shapes are not broadcast-compatible.")
         return float(np.prod(shape, dtype=np.float64)) * k, shape
 
-    n = len(ms)
+    n = len(shapes)
     op = [[None] * n for _ in range(n)]
     for i in range(n):
-        op[i][i] = (0.0, [int(s) for s in ms[i].shape])
+        op[i][i] = (0.0, [int(s) for s in shapes[i]])
     for length in range(2, n + 1):
         for i in range(0, n - length + 1):
             best, best_shape = float("inf"), None
@@ -102,9 +97,12 @@ def matmul(*matrices):
                 raise OverflowError("Integer overflow (too many FLOPs).")
             op[i][i + length - 1] = (best, best_shape)
 
+    plan = []
+
     def product(lo, hi):
         if lo == hi:
-            return ms[lo]
+            plan.append(lo)
+            return
         best, idx = float("inf"), None
         for i in range(lo, hi):
             lf, ls = op[lo][i]
@@ -113,9 +111,37 @@ def matmul(*matrices):
             f += lf + rf
             if f < best:
                 best, idx = f, i
-        return matmul2(product(lo, idx), product(idx + 1, hi))
+        product(lo, idx)
+        product(idx + 1, hi)
+        plan.append(-1)
 
-    return product(0, n - 1)
+    product(0, n - 1)
+    return plan, op[0][n - 1][1]
+
+
+def matmul(*matrices):
+    """Matrix-chain product (matmul.js:150-236): the flop-optimal parenthesisation is found on the host exactly as the
+    reference does; the products run on the GPU with every intermediate kept in HBM (nd4b_matmul_plan_f64)."""
+    ms = [asarray(m) for m in matrices]
+    if len(ms) == 1:
+        return ms[0]
+    if len(ms) == 2:
+        return matmul2(*ms)
+    for i, m in enumerate(ms):
+        if m.ndim < 2:
+            raise ValueError("A must be at least 2D." if i == 0 else "B must be at least 2D.")
+    plan, shape = _chain_plan([m.shape for m in ms])
+    data = [_f64(m, "matmul") for m in ms]
+    n = len(ms)
+    ptrs = (C.c_void_p * n)(*[d.ctypes.data for d in data])
+    shapes = [np.ascontiguousarray(m.shape, dtype=np.int32) for m in ms]
+    sptrs = (C.c_void_p * n)(*[sh.ctypes.data for sh in shapes])
+    ndims = (C.c_int * n)(*[m.ndim for m in ms])
+    plan_arr = np.asarray(plan, np.int32)
+    c_shape = np.asarray(shape, np.int32)
+    out = _new(c_shape)
+    _lib.check(_lib.load().nd4b_matmul_plan_f64(n, ptrs, sptrs, ndims, _ptr(plan_arr), len(plan), _ptr(out), _ptr(c_shape), len(c_shape)))
+    return NDArray(c_shape, out)
 
 
 def cholesky_decomp(S):
@@ -148,6 +174,22 @@ def qr_decomp(A):
     q, r = _new(q_shape), _new(r_shape)
     _lib.check(_lib.load().nd4b_qr_f64(_ptr(ad), _ptr(q), _ptr(r), ad.size // (rows * cols), rows, cols))
     return NDArray(q_shape, q), NDArray(r_shape, r)
+
+
+def _qr_decomp_inplace(A, Y):
+    """Batched form of nd4js `_qr_decomp_inplace(M,N,L, A,A_off, Y,Y_off)` (src/la/qr.js:147-183): returns `(R, QtY)` with
+    R[...,M,N] upper trapezoidal and QtY[...,M,L] = Q^T Y, without forming Q.  The reference mutates flat arrays in place;
+    NDArrays are values here, so the results are new arrays (same shapes as A and Y)."""
+    A, Y = asarray(A), asarray(Y)
+    if A.ndim < 2 or Y.ndim < 2:
+        raise ValueError("Assertion failed.")
+    m, n, l = int(A.shape[-2]), int(A.shape[-1]), int(Y.shape[-1])
+    ad, yd = _f64(A, "_qr_decomp_inplace"), _f64(Y, "_qr_decomp_inplace")
+    if int(Y.shape[-2]) != m or tuple(A.shape[:-2]) != tuple(Y.shape[:-2]):
+        raise ValueError("Assertion failed.")
+    r, qty = _new(np.array(A.shape, np.int32)), _new(np.array(Y.shape, np.int32))
+    _lib.check(_lib.load().nd4b_qr_inplace_f64(_ptr(ad), _ptr(yd), _ptr(r), _ptr(qty), ad.size // (m * n), m, n, l))
+    return NDArray(np.array(A.shape, np.int32), r), NDArray(np.array(Y.shape, np.int32), qty)
 
 
 def svd_jac_1sided(A):

@@ -254,6 +254,32 @@ static int ref_qr_tall_one(int N, int M, const double* A, double* Q, double* R) 
 }
 
 /* src/la/qr.js:80-145 */
+/* _qr_decomp_inplace(M,N,L, A,A_off, Y,Y_off): src/la/qr.js:147-183.  Givens elimination of A_ij (i > j) in the
+ * reference's order, the same rotations applied to the rows of Y; A ends as R (zeros below the diagonal), Y as Q^T Y. */
+static void ref_qr_inplace_one(int M, int N, int L, double* A, double* Y) {
+  for (int i = 1; i < M; i++)
+    for (int j = 0; j < N && j < i; j++) {
+      const int64_t ij = (int64_t)N * i + j, jj = (int64_t)N * j + j;
+      const double A_ij = A[ij];
+      if (0 == A_ij) continue;
+      double csn[3];
+      nd4ref_giv_rot_qr(A[jj], A_ij, csn);
+      A[ij] = 0;
+      if (0 == csn[1]) continue;
+      A[jj] = csn[2];
+      giv_rot_rows(A, N - 1 - j, jj + 1, ij + 1, csn[0], csn[1]);
+      giv_rot_rows(Y, L, (int64_t)L * j, (int64_t)L * i, csn[0], csn[1]);
+    }
+}
+
+int nd4ref_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY, int64_t batch, int M, int N, int L) {
+  if (!A || !Y || !R || !QtY || batch < 1 || M < 1 || N < 1 || L < 1) return ND4REF_E_SHAPE;
+  memcpy(R, A, sizeof(double) * (size_t)batch * M * N);
+  memcpy(QtY, Y, sizeof(double) * (size_t)batch * M * L);
+  for (int64_t b = 0; b < batch; b++) ref_qr_inplace_one(M, N, L, R + b * (int64_t)M * N, QtY + b * (int64_t)M * L);
+  return 0;
+}
+
 int nd4ref_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
   const int L = rows < cols ? rows : cols;
   for (int64_t b = 0; b < batch; b++) {

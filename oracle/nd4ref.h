@@ -55,6 +55,10 @@ int nd4ref_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_
  * Q is [batch,rows,min(rows,cols)], R is [batch,min(rows,cols),cols]. */
 int nd4ref_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols);
 
+/* _qr_decomp_inplace: src/la/qr.js:147-183, batched and out of place: R[batch,M,N] <- A rotated to upper trapezoidal form,
+ * QtY[batch,M,L] <- the same Givens rotations applied to Y. */
+int nd4ref_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY, int64_t batch, int M, int N, int L);
+
 /* svd_jac_2sided: src/la/svd_jac_2sided.js:30-144 + src/la/_svd_jac_utils.js:72-188.
  * U [batch,rows,L], sv [batch,L], V [batch,L,cols], L=min(rows,cols); A = U diag(sv) V.
  * sweeps_out (may be NULL) receives the maximum number of sweeps over the batch. */

@@ -47,6 +47,7 @@ def lib():
         L.nd4ref_matmul_f64.argtypes = [dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int]
         L.nd4ref_cholesky_f64.argtypes = [dp, dp, i64, C.c_int, C.POINTER(i64)]
         L.nd4ref_qr_f64.argtypes = [dp, dp, dp, i64, C.c_int, C.c_int]
+        L.nd4ref_qr_inplace_f64.argtypes = [dp, dp, dp, dp, i64, C.c_int, C.c_int, C.c_int]
         L.nd4ref_svd_jac2_f64.argtypes = [dp, dp, dp, dp, i64, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.nd4ref_tri_solve_f64.argtypes = [C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int]
         L.nd4ref_tri_solve_f64.restype = C.c_int
@@ -123,6 +124,20 @@ def qr_decomp(a):
     if rc:
         raise RefError(rc)
     return q, r
+
+
+def qr_decomp_inplace(a, y):
+    """_qr_decomp_inplace (src/la/qr.js:147-183) over a batch: returns (R, Q^T y)."""
+    a, y = _f64(a), _f64(y)
+    m, n = a.shape[-2:]
+    l = y.shape[-1]
+    batch = a.size // (m * n)
+    assert y.shape[-2] == m and y.size // (m * l) == batch
+    r, qty = np.empty_like(a), np.empty_like(y)
+    rc = lib().nd4ref_qr_inplace_f64(_dp(a), _dp(y), _dp(r), _dp(qty), batch, m, n, l)
+    if rc:
+        raise RefError(rc)
+    return r, qty
 
 
 def svd_jac_2sided(a, return_sweeps=False):

@@ -47,26 +47,49 @@ def test_argument_errors_carry_the_reference_texts():
         la.cholesky_decomp(np.ones((2, 2), np.float32))
 
 
-def test_matmul_chain_uses_the_flop_optimal_order(monkeypatch):
-    """matmul.js:185-235: for [10,2]x[2,10]x[10,2] the right product must be formed first."""
-    from nd4js_b200 import la, from_numpy
-    calls = []
+def test_matmul_chain_uses_the_flop_optimal_order():
+    """matmul.js:185-235: for [10,2]x[2,10]x[10,2] the right product must be formed first; the plan is the postfix form
+    handed to nd4b_matmul_plan_f64 (i pushes operand i, -1 multiplies the two topmost items)."""
+    from nd4js_b200 import la
 
-    def fake(a, b):
-        a, b = la.asarray(a), la.asarray(b)
-        calls.append((tuple(a.shape), tuple(b.shape)))
-        return from_numpy(a.numpy() @ b.numpy())
+    def run(plan, mats):  # the plan's semantics, in NumPy
+        st = []
+        for op in plan:
+            if op >= 0:
+                st.append(mats[op])
+            else:
+                b_ = st.pop()
+                a_ = st.pop()
+                st.append(a_ @ b_)
+        assert len(st) == 1
+        return st[0]
 
-    monkeypatch.setattr(la, "matmul2", fake)
     a, b, c = np.ones((10, 2)), np.ones((2, 10)), np.ones((10, 2))
-    out = la.matmul(a, b, c)
-    assert calls == [((2, 10), (10, 2)), ((10, 2), (2, 2))]
-    assert (out.numpy() == a @ b @ c).all()
-    calls.clear()
+    plan, shape = la._chain_plan([a.shape, b.shape, c.shape])
+    assert plan == [0, 1, 2, -1, -1] and shape == [10, 2]
+    plan, shape = la._chain_plan([(2, 10), (10, 2), (2, 10)])
+    assert plan == [0, 1, -1, 2, -1] and shape == [2, 10]
+    # broadcast-aware flop counts (matmul.js:159-180): a batched left factor makes the right-to-left order cheaper
+    plan, shape = la._chain_plan([(7, 4, 3), (3, 50), (50, 2)])
+    assert plan == [0, 1, 2, -1, -1] and shape == [7, 4, 2]
     g = np.load(os.path.join(ROOT, "tests", "golden", "known_answers.npz"))
-    out = la.matmul(g["chain_a"], g["chain_b"], g["chain_c"])
-    assert (out.numpy() == g["chain_abc"]).all()
-    assert la.matmul(a) is not None and len(calls) == 2
+    mats = [g["chain_a"], g["chain_b"], g["chain_c"]]
+    plan, _ = la._chain_plan([m.shape for m in mats])
+    assert (run(plan, mats) == g["chain_abc"]).all()
+    rng = np.random.default_rng(0)
+    for _ in range(20):  # any plan is a valid parenthesisation of the whole chain with the minimal flop count
+        n = int(rng.integers(3, 7))
+        dims = rng.integers(1, 9, n + 1)
+        mats = [rng.integers(-3, 4, (int(dims[i]), int(dims[i + 1]))).astype(np.float64) for i in range(n)]
+        plan, shape = la._chain_plan([m.shape for m in mats])
+        assert sorted(p for p in plan if p >= 0) == list(range(n)) and plan.count(-1) == n - 1
+        want = mats[0]
+        for m in mats[1:]:
+            want = want @ m
+        assert (run(plan, mats) == want).all() and list(want.shape) == shape
+    with pytest.raises(ValueError, match="Shape mismatch."):
+        la._chain_plan([(2, 3), (4, 5), (5, 6)])
+    assert la.matmul(a) is not None
 
 
 def test_shard_ranges_cover_the_batch():

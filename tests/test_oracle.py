@@ -222,3 +222,23 @@ def test_qr_lstsq_vs_lapack(ref):
     x = ref.qr_lstsq(q, r, y)
     for b in range(3):
         np.testing.assert_allclose(x[b], np.linalg.lstsq(a[b], y[b], rcond=None)[0], atol=1e-13)
+
+
+@pytest.mark.parametrize("shape", [(3, 7, 4, 2), (2, 4, 4, 3), (2, 3, 6, 1), (1, 1, 1, 1)])
+def test_qr_decomp_inplace_restatement(ref, shape):
+    # src/la/qr.js:147-183: Givens rotations are orthogonal, so (Q^T y) and R solve the same least-squares problem as (A, y):
+    # R upper trapezoidal with exact zeros, R^T R = A^T A, R^T (Q^T y) = A^T y, |Q^T y|_F = |y|_F, and the thin factor
+    # agrees with qr_decomp's R up to row signs
+    b, m, n, l = shape
+    a, y = uniform(31, (b, m, n)), uniform(32, (b, m, l))
+    r, qty = ref.qr_decomp_inplace(a, y)
+    assert r.shape == a.shape and qty.shape == y.shape
+    assert (np.tril(r, -1) == 0).all()
+    at = np.swapaxes(a, -1, -2)
+    rt = np.swapaxes(r, -1, -2)
+    np.testing.assert_allclose(rt @ r, at @ a, atol=1e-13)
+    np.testing.assert_allclose(rt @ qty, at @ y, atol=1e-13)
+    np.testing.assert_allclose(np.linalg.norm(qty, axis=(-2, -1)), np.linalg.norm(y, axis=(-2, -1)), rtol=1e-14)
+    k = min(m, n)
+    _, r2 = ref.qr_decomp(a)
+    np.testing.assert_allclose(np.abs(r[..., :k, :]), np.abs(r2), atol=1e-13)
