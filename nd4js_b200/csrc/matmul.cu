@@ -261,9 +261,9 @@ gemm_tiled_kernel(const double* __restrict__ A, const double* __restrict__ B, do
 // the edges) through a STAGES-deep ring, so global latency is hidden behind the DMMA stream instead of being
 // exposed at every k-tile.  This is the kernel behind the compute-bound figures (C1 and the large-N probes).
 // ------------------------------------------------------------------------------------------------
-template <int WR, int WC, int TM, int TN, int STAGES>
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
 struct PipeCfg {
-  static constexpr int BM = WR * TM * 8, BN = WC * TN * 8, BK = 16;
+  static constexpr int BM = WR * TM * 8, BN = WC * TN * 8, BK = BK_;
   static constexpr int LDA = BK + 4, LDB = BN + 4;
   static constexpr int THREADS = WR * WC * 32;
   static constexpr int A_CHUNKS = BM * BK / 2, B_CHUNKS = BK * BN / 2;  // 16-byte chunks per tile
@@ -278,11 +278,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-template <int WR, int WC, int TM, int TN, int STAGES>
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
 __global__ void __launch_bounds__(WR * WC * 32)
 gemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                  int64_t batch, int I, int K, int J, BatchMap map, int tiles_m, int tiles_n) {
-  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES>;
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, T = Cfg::THREADS;
   extern __shared__ __align__(16) double gemm_smem[];
 
@@ -369,14 +369,14 @@ gemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, dou
   }
 }
 
-template <int WR, int WC, int TM, int TN, int STAGES>
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
 static cudaError_t launch_pipe(cudaStream_t s, const double* A, const double* B, double* C,
                                int64_t batch, int I, int K, int J, const BatchMap& map) {
-  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES>;
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_>;
   const int tiles_m = (I + Cfg::BM - 1) / Cfg::BM, tiles_n = (J + Cfg::BN - 1) / Cfg::BN;
   const int64_t grid = batch * tiles_m * tiles_n;
   if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  auto kern = gemm_pipe_kernel<WR, WC, TM, TN, STAGES>;
+  auto kern = gemm_pipe_kernel<WR, WC, TM, TN, STAGES, BK_>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -427,7 +427,9 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
     if (I >= 48 && J >= 48 && t64 >= 2LL * sm_count) return launch_pipe<2, 2, 4, 4, 4>(s, A, B, C, batch, I, K, J, map);
     if (I >= 48 && J >= 24) {
       // few tiles (e.g. one 512^3): 32x32 tiles with 4 warps of 16x16 put >= 2 CTAs on most SMs
-      // measured on one 512^3: 64x32 tiles/4 warps 18.7 us, 64x32/8 warps 17.6 us, 32x32/4 warps (256 CTAs) 16.4 us
+      // measured on one 512^3: 64x32 tiles/4 warps 18.7 us, 64x32/8 warps 17.6 us, 32x32/4 warps (256 CTAs) 16.4 us;
+      // a second sweep (BK 16/32/64, 2-4 stages, 32x32 / 64x32 / 32x64 tiles, 4 or 8 warps) stayed within 15.4-18.6 us:
+      // at this size the time is fill + wave quantisation (108 SMs hold two CTAs, 40 hold one), not the tile shape
       const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
       if (t6432 < 2LL * sm_count) return launch_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
       return launch_pipe<4, 1, 2, 4, 4>(s, A, B, C, batch, I, K, J, map);
