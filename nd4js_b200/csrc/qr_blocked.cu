@@ -140,10 +140,12 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
       else { d00 = fma(v.x, a[P][j][0], d00); d10 = fma(v.y, a[P][j][1], d10); }
     }
     double d = (d00 + d01) + (d10 + d11);
-    // |x|^2 over rows >= k: the four partial sums of the pivot quad, fetched in parallel
-    const double s = (shfl(d, 4 * kk) + shfl(d, 4 * kk + 1)) + (shfl(d, 4 * kk + 2) + shfl(d, 4 * kk + 3));
+    // quad totals, then |x|^2 (rows >= k) from the pivot quad.  (Fetching the pivot quad's four partial sums in parallel
+    // shortens the chain by two shuffle latencies but costs six more SHFL: the panel phase is bound by the shared-memory /
+    // shuffle pipe of the SM — 12 warps, ~90 pipe cycles per step each — not by the length of the chain.)
     d += shfl_xor(d, 1);
     d += shfl_xor(d, 2);
+    const double s = shfl(d, 4 * kk);
     const int e0 = kk & 1, t0 = kk >> 1;
     const double akj = shfl(e0 ? a[P][P][1] : a[P][P][0], (lane & ~3) | t0);  // my column's element in the pivot row
     const bool ok = s > 0x1p-900;  // else a (numerically) zero column: H = I
@@ -334,7 +336,7 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
   }
 }
 
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, bool REREAD>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch) {
   extern __shared__ __align__(16) double qb_smem[];
@@ -394,10 +396,10 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   double* r_out = R + m * 1024;
   unsigned sgn[4];
   QB_MARK(0);
-  qb_r_phase<0, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm);
-  qb_r_phase<1, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm);
-  qb_r_phase<2, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm);
-  qb_r_phase<3, (MINB * WARPS > 8)>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm);
+  qb_r_phase<0, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm);
+  qb_r_phase<1, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm);
+  qb_r_phase<2, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm);
+  qb_r_phase<3, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm);
 
   qb_q_phase<3>(a, vs, ts, lane, g, t);
   qb_q_phase<2>(a, vs, ts, lane, g, t);
@@ -430,28 +432,28 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
 
 }  // namespace
 
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, bool REREAD>
 static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch) {
   static bool attr_set[64] = {false};
   constexpr size_t smem = sizeof(double) * kQbWarpDoubles * WARPS;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB, REREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  qr64x32_blocked_kernel<WARPS, MINB><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(A, Q, R, batch);
+  qr64x32_blocked_kernel<WARPS, MINB, REREAD><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(A, Q, R, batch);
   return cudaGetLastError();
 }
 
 // variant 2: two CTAs per SM (216 registers, no spills, pivot column kept in registers) instead of three (168 registers,
-// idle column blocks parked in local memory around the panel loops): 1.43 vs 1.38 ms on C4.  Phase-locking the warps of
+// idle column blocks parked in local memory around the panel loops, pivot column read twice from shared memory): 1.38 vs 1.27 ms on C4.  Phase-locking the warps of
 // a sub-partition with named barriers (so that no DMMA stream runs beside a panel chain) was measured slower (1.55-1.70 ms):
 // the panel chains of the locked warps then collide on the shared-memory pipe instead.
 cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int variant) {
-  if (variant == 2) return qb_launch<4, 2>(s, A, Q, R, batch);
-  return qb_launch<4, 3>(s, A, Q, R, batch);
+  if (variant == 2) return qb_launch<4, 2, false>(s, A, Q, R, batch);
+  return qb_launch<4, 3, true>(s, A, Q, R, batch);
 }
 
 }  // namespace nd4b
