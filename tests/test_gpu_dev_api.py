@@ -1,0 +1,139 @@
+"""Device-resident entry points (`nd4b_dev_*`, include/nd4b.h): the forms the bench times and a caller composes on its
+own stream.  Inputs live in HBM (torch is only the allocator here), results are checked against the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import spd, uniform
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dev(la):
+    import torch
+    from nd4js_b200 import _lib
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    class Dev:
+        pass
+
+    d = Dev()
+    d.torch, d.lib, d.stream = torch, lib, C.c_void_p(stream)
+    d.up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d.p = lambda t: C.c_void_p(t.data_ptr())
+
+    def ok(rc):
+        assert rc == 0, lib.nd4b_last_error().decode()
+        torch.cuda.synchronize()
+
+    d.ok = ok
+    return d
+
+
+def _sign_normalise(q, r):
+    sg = np.where(np.diagonal(r, axis1=-2, axis2=-1) < 0, -1.0, 1.0)
+    return q * sg[..., None, :], r * sg[..., :, None]
+
+
+def test_dev_matmul_strides_and_broadcast(dev, ref):
+    a, b = uniform(1, (37, 32, 32)), uniform(2, (37, 32, 32))
+    da, db = dev.up(a), dev.up(b)
+    out = dev.torch.empty(37, 32, 32, dtype=dev.torch.float64, device="cuda")
+    dev.ok(dev.lib.nd4b_dev_matmul_f64(0, dev.stream, dev.p(da), 1024, dev.p(db), 1024, dev.p(out), 37, 32, 32, 32))
+    want = ref.matmul2(a, b)
+    assert np.max(np.abs(out.cpu().numpy() - want) / (np.abs(a) @ np.abs(b))) <= TOL
+    # stride 0: one B for the whole batch (matmul.js:59-67 with a batch dim of 1)
+    dev.ok(dev.lib.nd4b_dev_matmul_f64(0, dev.stream, dev.p(da), 1024, dev.p(db), 0, dev.p(out), 37, 32, 32, 32))
+    want = ref.matmul2(a, b[:1])
+    assert np.max(np.abs(out.cpu().numpy() - want) / (np.abs(a) @ np.abs(b[:1]))) <= TOL
+    # a general shape through the tiled kernels
+    a2, b2 = uniform(3, (5, 70, 33)), uniform(4, (5, 33, 18))
+    out2 = dev.torch.empty(5, 70, 18, dtype=dev.torch.float64, device="cuda")
+    da2, db2 = dev.up(a2), dev.up(b2)
+    dev.ok(dev.lib.nd4b_dev_matmul_f64(0, dev.stream, dev.p(da2), 70 * 33, dev.p(db2), 33 * 18, dev.p(out2), 5, 70, 33, 18))
+    assert np.max(np.abs(out2.cpu().numpy() - ref.matmul2(a2, b2)) / (np.abs(a2) @ np.abs(b2))) <= TOL
+
+
+def test_dev_cholesky_and_failure_key(dev, ref):
+    s = spd(5, (100,), 16)
+    s[41, 7, 7] = -1.0  # not positive definite: the factorisation of matrix 41 fails
+    ds = dev.up(s)
+    out = dev.torch.empty_like(ds)
+    info = dev.torch.full((1,), 2 ** 62, dtype=dev.torch.int64, device="cuda")
+    dev.ok(dev.lib.nd4b_dev_cholesky_f64(0, dev.stream, dev.p(ds), dev.p(out), 100, 16, dev.p(info)))
+    assert int(info.item()) >> 1 == 41 and int(info.item()) & 1 == 1  # key = 2*index + (singular ? 1 : 0)
+    good = np.delete(np.arange(100), 41)
+    assert (out.cpu().numpy()[good] == ref.cholesky_decomp(s[good])).all()
+
+
+@pytest.mark.parametrize("offset", [0, 1])
+def test_dev_qr_64x32_aligned_and_unaligned(dev, ref, offset):
+    # offset 1 shifts every pointer by 8 bytes: the blocked kernel must leave its 16-byte TMA bulk path (A, Q) for plain loads
+    a = uniform(6, (33, 64, 32))
+    buf_a = dev.torch.empty(a.size + 2, dtype=dev.torch.float64, device="cuda")
+    buf_q = dev.torch.empty(a.size + 2, dtype=dev.torch.float64, device="cuda")
+    buf_r = dev.torch.empty(33 * 32 * 32 + 2, dtype=dev.torch.float64, device="cuda")
+    da, dq, dr = buf_a[offset:offset + a.size], buf_q[offset:offset + a.size], buf_r[offset:offset + 33 * 1024]
+    da.copy_(dev.up(a).reshape(-1))
+    assert da.data_ptr() % 16 == 8 * offset
+    dev.ok(dev.lib.nd4b_dev_qr_f64(0, dev.stream, dev.p(da), dev.p(dq), dev.p(dr), 33, 64, 32, None, 0))
+    q, r = dq.cpu().numpy().reshape(33, 64, 32), dr.cpu().numpy().reshape(33, 32, 32)
+    qn, rn = _sign_normalise(*ref.qr_decomp(a))
+    assert (np.tril(r, -1) == 0).all() and np.max(np.abs(q - qn)) <= TOL and np.max(np.abs(r - rn)) <= TOL
+
+
+def test_dev_qr_generic_shape_needs_its_workspace(dev, ref):
+    a = uniform(7, (9, 20, 7))
+    need = dev.lib.nd4b_dev_qr_workspace(9, 20, 7)
+    assert need > 0 and dev.lib.nd4b_dev_qr_workspace(9, 64, 32) == 0
+    da = dev.up(a)
+    dq = dev.torch.empty(9, 20, 7, dtype=dev.torch.float64, device="cuda")
+    dr = dev.torch.empty(9, 7, 7, dtype=dev.torch.float64, device="cuda")
+    assert dev.lib.nd4b_dev_qr_f64(0, dev.stream, dev.p(da), dev.p(dq), dev.p(dr), 9, 20, 7, None, 0) != 0  # no workspace
+    work = dev.torch.empty(need // 8 + 1, dtype=dev.torch.float64, device="cuda")
+    dev.ok(dev.lib.nd4b_dev_qr_f64(0, dev.stream, dev.p(da), dev.p(dq), dev.p(dr), 9, 20, 7, dev.p(work), C.c_size_t(need)))
+    qn, rn = _sign_normalise(*ref.qr_decomp(a))
+    assert np.max(np.abs(dq.cpu().numpy() - qn)) <= TOL and np.max(np.abs(dr.cpu().numpy() - rn)) <= TOL
+
+
+def test_dev_qr_inplace(dev, ref):
+    a, y = uniform(8, (12, 10, 4)), uniform(9, (12, 10, 3))
+    dr = dev.torch.empty(12, 10, 4, dtype=dev.torch.float64, device="cuda")
+    dy = dev.torch.empty(12, 10, 3, dtype=dev.torch.float64, device="cuda")
+    da, dyin = dev.up(a), dev.up(y)
+    dev.ok(dev.lib.nd4b_dev_qr_inplace_f64(0, dev.stream, dev.p(da), dev.p(dyin), dev.p(dr), dev.p(dy), 12, 10, 4, 3))
+    r, qty = dr.cpu().numpy(), dy.cpu().numpy()
+    rref, qref = ref.qr_decomp_inplace(a, y)
+    sg = np.sign(np.diagonal(rref, axis1=-2, axis2=-1))
+    sg[sg == 0] = 1.0
+    assert (np.tril(r, -1) == 0).all()
+    assert np.max(np.abs(r[:, :4] - sg[..., None] * rref[:, :4])) <= TOL
+    assert np.max(np.abs(qty[:, :4] - sg[..., None] * qref[:, :4])) <= TOL
+
+
+def test_dev_svd_sweeps_and_sweep_counter(dev, ref):
+    a = uniform(10, (24, 64, 64))
+    da = dev.up(a)
+    u = dev.torch.empty(24, 64, 64, dtype=dev.torch.float64, device="cuda")
+    sv = dev.torch.empty(24, 64, dtype=dev.torch.float64, device="cuda")
+    v = dev.torch.empty(24, 64, 64, dtype=dev.torch.float64, device="cuda")
+    sweeps = dev.torch.zeros(1, dtype=dev.torch.int32, device="cuda")
+    total = dev.torch.zeros(1, dtype=dev.torch.int64, device="cuda")
+    dev.ok(dev.lib.nd4b_dev_svd_sweep_counter(0, dev.p(total)))
+    try:
+        for _ in range(2):
+            dev.ok(dev.lib.nd4b_dev_svd_jac1_f64(0, dev.stream, dev.p(da), dev.p(u), dev.p(sv), dev.p(v), 24, 64, 64, dev.p(sweeps), None, 0))
+    finally:
+        dev.ok(dev.lib.nd4b_dev_svd_sweep_counter(0, None))
+    smax, ssum = int(sweeps.item()), int(total.item())
+    assert 5 <= smax <= 15 and 2 * 24 * 5 <= ssum <= 2 * 24 * smax and ssum % 2 == 0  # two identical launches were counted
+    dev.ok(dev.lib.nd4b_dev_svd_jac1_f64(0, dev.stream, dev.p(da), dev.p(u), dev.p(sv), dev.p(v), 24, 64, 64, None, None, 0))
+    assert int(total.item()) == ssum  # counter switched off
+    _, sref, _ = ref.svd_jac_2sided(a)
+    s = sv.cpu().numpy()
+    assert np.max(np.abs(s - sref)) <= TOL * sref.max()
+    assert np.max(np.abs((u.cpu().numpy() * s[:, None, :]) @ v.cpu().numpy() - a)) <= 64 * TOL
