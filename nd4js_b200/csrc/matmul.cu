@@ -424,12 +424,15 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
     const int64_t t128 = batch * ((I + 127) / 128) * ((J + 127) / 128);
     const int64_t t64 = batch * ((I + 63) / 64) * ((J + 63) / 64);
     if (I >= 96 && J >= 96 && t128 >= sm_count) return launch_pipe<2, 4, 8, 4, 3>(s, A, B, C, batch, I, K, J, map);
-    if (I >= 48 && J >= 48 && t64 >= 2LL * sm_count) return launch_pipe<2, 2, 4, 4, 4>(s, A, B, C, batch, I, K, J, map);
+    // 64x64 tiles from 1.5 CTAs per SM on (1024^3 = 256 tiles: 80 us vs 101 us with 64x32 tiles)
+    if (I >= 48 && J >= 48 && 2 * t64 >= 3LL * sm_count) return launch_pipe<2, 2, 4, 4, 4>(s, A, B, C, batch, I, K, J, map);
     if (I >= 48 && J >= 24) {
       // few tiles (e.g. one 512^3): 32x32 tiles with 4 warps of 16x16 put >= 2 CTAs on most SMs
       // measured on one 512^3: 64x32 tiles/4 warps 18.7 us, 64x32/8 warps 17.6 us, 32x32/4 warps (256 CTAs) 16.4 us;
       // a second sweep (BK 16/32/64, 2-4 stages, 32x32 / 64x32 / 32x64 tiles, 4 or 8 warps) stayed within 15.4-18.6 us:
-      // at this size the time is fill + wave quantisation (108 SMs hold two CTAs, 40 hold one), not the tile shape
+      // at this size the time is fill + wave quantisation (108 SMs hold two CTAs, 40 hold one), not the tile shape.
+      // Split-K over a 2- or 4-CTA cluster with a DSMEM reduction (64x64 tiles, 128 / 256 CTAs) was built and measured:
+      // 18.9 / 20.9 us — a 64x64 CTA of 4 warps alone on an SM runs its main loop at ~52 % of the DMMA peak.
       const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
       if (t6432 < 2LL * sm_count) return launch_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
       return launch_pipe<4, 1, 2, 4, 4>(s, A, B, C, batch, I, K, J, map);
