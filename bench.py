@@ -368,6 +368,21 @@ def run_ours(args):
 
     line = None
     if rank == 0:
+        kernel = {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
+                  "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel"}[args.workload]
+        traffic, traffic_src = NCU_TRAFFIC_BYTES.get(args.workload, (None, None))
+        if args.workload in ("c1", "g4k", "c5"):
+            # compute-bound configs: against the FP64 pipe — DMMA for the GEMMs, DFMA for the Jacobi SVD; both
+            # instruction kinds share one pipe and one peak on B200
+            tflops = value / world * flop_unit / 1e12
+            roofline = {"bound": "tensor", "achieved": tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                        "frac": tflops / FP64_PEAK_TFLOPS, "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": "measured FP64 pipe peak (profiles/r01_fp64_peak.json: DMMA.8x8x4 37.15, DFMA 36.83 TFLOP/s)",
+                        "kernel": kernel, "algorithmic_flop_per_unit": flop_unit, "units_per_launch": units}
+        else:
+            roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_unit": bpu, "units_per_launch": units}
         line = {
             "metric": "matrices/s", "value": value, "unit": "matrices/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * launch_s, "higher_is_better": True, "scaling": "weak",
@@ -380,12 +395,7 @@ def run_ours(args):
                     "steps": e2e_steps, "timing": "host wall clock around the blocking C-ABI call, barrier+sync both sides, max over ranks",
                     "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1"}[args.workload]},
             "gpu_launches": args.steps + int(e2e_launches),
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[0],
-                         "traffic_source": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[1], "peak_source": peak_src,
-                         "kernel": {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
-                                    "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel"}[args.workload],
-                         "algorithmic_bytes_per_unit": bpu, "units_per_launch": units},
+            "roofline": roofline,
             "clocks": clocks,
         }
         if sweeps:
