@@ -36,6 +36,8 @@ WORKLOADS = {
     "c3": ("batched nd.la.cholesky_decomp float64 SPD [262144,16,16]", 262144, 4096, 16 ** 3 / 3.0),
     "c4": ("batched nd.la.qr_decomp float64 [65536,64,32] Householder", 65536, 40960, 2 * (2 * 64 * 32 * 32 - 2 * 32 ** 3 / 3.0)),
     "c5": ("batched nd.la.svd_jac_1sided float64 [16384,64,64]", 16384, 98816, 2016 * 1152),  # flop per sweep
+    # next row 8f-1: the solve that follows C3 (one right-hand side per matrix); bytes: L read whole + y in + x out
+    "s3": ("batched nd.la.cholesky_solve float64 L[262144,16,16], y[262144,16,1]", 262144, 2048 + 128 + 128, 2 * 16 * 16),
     # compute-bound probe of the same matmul kernel family (north_star: matmul vs FP64 tensor-core peak)
     "g4k": ("nd.la.matmul float64 4096x4096 . 4096x4096 single matrix (compute-bound probe)", 1, 3 * 4096 * 4096 * 8, 2 * 4096 ** 3),
 }
@@ -122,7 +124,7 @@ def run_reference(args):
     nd4ref.build()
     desc, units, bpu, fpu = WORKLOADS[args.workload]
     rng = np.random.default_rng(3)
-    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24, "g4k": 1}[args.workload]
+    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24, "g4k": 1, "s3": 65536}[args.workload]
     fn, data = _ref_case(args.workload, sample, rng, nd4ref)
     for _ in range(min(args.warmup, 1)):
         fn(*data)
@@ -158,6 +160,9 @@ def _ref_case(name, n, rng, nd4ref):
         return nd4ref.cholesky_decomp, (g @ g.transpose(0, 2, 1) + 16 * np.eye(16),)
     if name == "c4":
         return nd4ref.qr_decomp, (rng.uniform(-1, 1, (n, 64, 32)),)
+    if name == "s3":
+        g = rng.uniform(-1, 1, (n, 16, 16))
+        return nd4ref.cholesky_solve, (np.linalg.cholesky(g @ g.transpose(0, 2, 1) + 16 * np.eye(16)), rng.uniform(-1, 1, (n, 16, 1)))
     return nd4ref.svd_jac_2sided, (rng.uniform(-1, 1, (n, 64, 64)),)
 
 
@@ -184,6 +189,12 @@ class DeviceCase:
             del gmat
             self.out = [torch.empty(units, 16, 16, **f64)]
             self.info = torch.full((1,), 2 ** 62, dtype=torch.int64, device="cuda")
+        elif name == "s3":
+            gmat = u(units, 16, 16)
+            self.a = torch.linalg.cholesky(torch.baddbmm(16.0 * torch.eye(16, **f64).expand(units, 16, 16), gmat, gmat.transpose(1, 2)))
+            del gmat
+            self.b = u(units, 16, 1)
+            self.out = [torch.empty(units, 16, 1, **f64)]
         elif name == "c4":
             self.a = u(units, 64, 32)
             self.out = [torch.empty(units, 64, 32, **f64), torch.empty(units, 32, 32, **f64)]
@@ -217,6 +228,8 @@ class DeviceCase:
             rc = L.nd4b_dev_matmul_f64(d, s, p(self.a), 1024, p(self.b), 1024, p(self.out[0]), self.units, 32, 32, 32)
         elif self.name == "c3":
             rc = L.nd4b_dev_cholesky_f64(d, s, p(self.a), p(self.out[0]), self.units, 16, p(self.info))
+        elif self.name == "s3":
+            rc = L.nd4b_dev_tri_solve_f64(d, s, 2, p(self.a), 256, p(self.b), 16, p(self.out[0]), self.units, 16, 1)
         elif self.name == "c4":
             rc = L.nd4b_dev_qr_f64(d, s, p(self.a), p(self.out[0]), p(self.out[1]), self.units, 64, 32, None, 0)
         else:
@@ -267,6 +280,14 @@ def host_case(name, nd, units):
         s, l = pinned((units, 16, 16), g @ g.transpose(0, 2, 1) + 16 * np.eye(16)), pinned((units, 16, 16))
         bad = C.c_int64(0)
         return (lambda: L.nd4b_cholesky_f64(p(s), p(l), units, 16, C.byref(bad))), s.numel() * 8, l.numel() * 8, (s, l)
+    if name == "s3":
+        g = rng.uniform(-1, 1, (units, 16, 16))
+        l = pinned((units, 16, 16), np.linalg.cholesky(g @ g.transpose(0, 2, 1) + 16 * np.eye(16)))
+        y, x = pinned((units, 16, 1), rng.uniform(-1, 1, (units, 16, 1))), pinned((units, 16, 1))
+        ls, ys = np.asarray((units, 16, 16), np.int32), np.asarray((units, 16, 1), np.int32)
+        lp, yp = C.c_void_p(ls.ctypes.data), C.c_void_p(ys.ctypes.data)
+        return ((lambda: L.nd4b_tri_solve_f64(2, p(l), lp, 3, p(y), yp, 3, p(x), yp, 3)), (l.numel() + y.numel()) * 8, x.numel() * 8,
+                (l, y, x, ls, ys))
     if name == "c4":
         a, q, r = pinned((units, 64, 32), rng.uniform(-1, 1, (units, 64, 32))), pinned((units, 64, 32)), pinned((units, 32, 32))
         return (lambda: L.nd4b_qr_f64(p(a), p(q), p(r), units, 64, 32)), a.numel() * 8, (q.numel() + r.numel()) * 8, (a, q, r)
@@ -369,7 +390,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         kernel = {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
-                  "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel"}[args.workload]
+                  "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel", "s3": "trisolve16_kernel"}[args.workload]
         traffic, traffic_src = NCU_TRAFFIC_BYTES.get(args.workload, (None, None))
         if args.workload in ("c1", "g4k", "c5"):
             # compute-bound configs: against the FP64 pipe — DMMA for the GEMMs, DFMA for the Jacobi SVD; both
@@ -393,7 +414,7 @@ def run_ours(args):
             "gflops": value * flop_unit / 1e9,
             "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timing": "host wall clock around the blocking C-ABI call, barrier+sync both sides, max over ranks",
-                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1"}[args.workload]},
+                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1", "s3": "tri_solve"}[args.workload]},
             "gpu_launches": args.steps + int(e2e_launches),
             "roofline": roofline,
             "clocks": clocks,
@@ -413,7 +434,7 @@ def run_ours(args):
     # ---------------- the other BASELINE configs, kernel-only, short ----------------
     if args.workload == "c2" and not args.no_others:
         others = {}
-        for name in ("c1", "g4k", "c3", "c4", "c5"):
+        for name in ("c1", "g4k", "c3", "s3", "c4", "c5"):
             d2, u2, b2, f2 = WORKLOADS[name]
             c2 = DeviceCase(name, torch, lib, local, u2)
             barrier()
@@ -439,7 +460,7 @@ def run_ours(args):
         import numpy as np
         from oracle import nd4ref
         nd4ref.build()
-        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96, "g4k": 1}[args.workload]
+        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96, "g4k": 1, "s3": 262144}[args.workload]
         fn, data = _ref_case(args.workload, sample, np.random.default_rng(3), nd4ref)
         reps, t0 = 0, time.perf_counter()
         while True:

@@ -147,6 +147,9 @@ int nd4b_dev_cholesky_f64(int device, void* stream, const double* S, double* L,
                           int64_t batch, int n, long long* info);
 int nd4b_dev_qr_f64(int device, void* stream, const double* A, double* Q, double* R,
                     int64_t batch, int rows, int cols, double* workspace, size_t workspace_bytes);
+/* op as in nd4b_tri_solve_f64; T[m*t_stride] is M x M, Y[m*y_stride] is M x J (strides in elements, 0 broadcasts), X[batch,M,J]. */
+int nd4b_dev_tri_solve_f64(int device, void* stream, int op, const double* T, int64_t t_stride, const double* Y, int64_t y_stride,
+                           double* X, int64_t batch, int M, int J);
 int nd4b_dev_qr_inplace_f64(int device, void* stream, const double* A, const double* Y, double* R, double* QtY,
                             int64_t batch, int M, int N, int L);
 /* sweeps (device int32, may be NULL): atomicMax of sweeps used.  workspace as reported below. */

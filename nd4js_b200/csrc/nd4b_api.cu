@@ -945,6 +945,19 @@ int nd4b_dev_qr_f64(int device, void* stream, const double* A, double* Q, double
   return check_cuda_launch(nd4b::launch_qr((cudaStream_t)stream, A, Q, R, batch, rows, cols, workspace, workspace_bytes), ctx);
 }
 
+int nd4b_dev_tri_solve_f64(int device, void* stream, int op, const double* T, int64_t t_stride, const double* Y, int64_t y_stride,
+                           double* X, int64_t batch, int M, int J) {
+  if (op < 0 || op > 2 || !T || !Y || !X || batch < 1 || M < 1 || J < 1 || t_stride < 0 || y_stride < 0)
+    return fail(ND4B_E_ARG, "dev_tri_solve: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  BatchMap map;
+  memset(&map, 0, sizeof map);
+  map.a_lin = t_stride;
+  map.b_lin = y_stride;
+  return check_cuda_launch(nd4b::launch_tri_solve((cudaStream_t)stream, op, T, Y, X, batch, M, J, map), ctx);
+}
+
 int nd4b_dev_qr_inplace_f64(int device, void* stream, const double* A, const double* Y, double* R, double* QtY,
                             int64_t batch, int M, int N, int L) {
   if (!A || !Y || !R || !QtY || batch < 1 || M < 1 || N < 1 || L < 1) return fail(ND4B_E_ARG, "dev_qr_inplace: bad argument");

@@ -67,9 +67,182 @@ tri_solve_kernel(int op, const double* __restrict__ T, const double* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// M = 16 (the solves that follow C3): 4 threads per matrix, 8 matrices per warp, like chol16_kernel.  The referenced
+// triangles of the warp's 8 matrices are staged in shared memory in packed form (136 entries + the 16 hoisted
+// reciprocals of the diagonal; matrix stride 156 doubles: the rows a quad reads at once and the matrices of a warp fall
+// into distinct banks) — 1.2 KB per matrix, so that 20 warps = 160 matrices are in flight per SM.  Thread t owns rows
+// t, t+4, t+8, t+12 of the right-hand side.  The substitution runs right-looking: as soon as x_k is known every row
+// subtracts t_ik * x_k, so the rows proceed in parallel while each entry still sees the reference's own sequence —
+// k ascending (forward) or descending (backward), product and difference rounded separately, IEEE division (hoisted
+// reciprocal of div.rn's fast path, common.cuh) — and X stays bit-identical.  JB right-hand sides are carried at once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTs16Warps = 4;
+constexpr int kTsMS = 156;   // doubles per matrix: 136 packed triangle entries, 16 reciprocals, 4 pad (156 = 12 mod 16)
+constexpr size_t kTs16Smem = sizeof(double) * kTs16Warps * 8 * kTsMS;
+
+// packed position of T[i][k]: lower triangle row-major (k <= i), or upper triangle row-major (k >= i)
+template <bool UPPER>
+__device__ __forceinline__ constexpr int ts_idx(int i, int k) {
+  return UPPER ? 16 * i - i * (i - 1) / 2 + (k - i) : i * (i + 1) / 2 + k;
+}
+
+__device__ __noinline__ double ts_ieee_div(double a, double b) { return a / b; }  // rare path, out of line
+
+// x_k = s_k / t_kk for JB right-hand sides: the owner's partial sums are fetched from its lane, the quotient is formed from
+// the precomputed reciprocal (bit-identical with `/` inside the fast-path ranges, else the full division)
+template <int JB>
+__device__ __forceinline__ void ts_divide(double (&xk)[JB], const double (&sk)[JB], int src_lane, double tkk, double y2) {
+  ColRecip rc;
+  rc.b = tkk;
+  rc.y = y2;
+  rc.bhi = __int_as_float(__double2hiint(tkk));
+  double num[JB];
+  bool ok = true;
+#pragma unroll
+  for (int jb = 0; jb < JB; jb++) {
+    num[jb] = shfl(sk[jb], src_lane);
+    xk[jb] = div_col(num[jb], rc, ok);
+  }
+  if (!ok) {
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++) xk[jb] = ts_ieee_div(num[jb], tkk);
+  }
+}
+
+template <int OP, int JB>
+__global__ void __launch_bounds__(kTs16Warps * 32)
+trisolve16_kernel(const double* __restrict__ T, const double* __restrict__ Y, double* __restrict__ X,
+                  int64_t batch, int J, BatchMap map) {
+  constexpr int N = 16;
+  constexpr bool UPPER = (OP == 1);
+  extern __shared__ __align__(16) double ts_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = lane & 3, q = lane >> 2, qbase = lane & ~3;
+  double* tile = ts_smem + warp * 8 * kTsMS;
+  const int64_t m0 = ((int64_t)blockIdx.x * kTs16Warps + warp) * 8;
+  if (m0 >= batch) return;  // warp-uniform
+  const int nmat = (int)min((int64_t)8, batch - m0);
+  const bool valid = q < nmat;
+  const int64_t m = m0 + (valid ? q : 0);
+  int64_t to, yo;
+  decode_batch2(map, m, to, yo);
+
+  // stage the referenced triangle of the 8 matrices, packed (8-byte async copies: the rows of a triangle are short)
+  {
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+#pragma unroll 1
+    for (int mm = 0; mm < nmat; mm++) {
+      const int64_t tmm = __shfl_sync(kFull, to, 4 * mm);
+      const double* src = T + tmm;
+#pragma unroll
+      for (int e = lane; e < N * N; e += 32) {
+        const int i = e >> 4, k = e & 15;
+        if (UPPER ? (k >= i) : (k <= i))
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_s + (uint32_t)(mm * kTsMS + ts_idx<UPPER>(i, k)) * 8u), "l"(src + e) : "memory");
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+  }
+  double* mine = tile + (valid ? q : 0) * kTsMS;
+  // reciprocals of the diagonal, off the substitution chain
+  if (valid) {
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int i = t + 4 * s;
+      mine[136 + i] = col_recip(mine[ts_idx<UPPER>(i, i)]).y;
+    }
+  }
+  __syncwarp();
+  const double* y = Y + yo;
+  double* x = X + m * (int64_t)(N * J);
+
+#pragma unroll 1
+  for (int j0 = 0; j0 < J; j0 += JB) {
+    double sv[4][JB];
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int jb = 0; jb < JB; jb++) sv[s][jb] = (j0 + jb < J) ? y[(int64_t)(t + 4 * s) * J + j0 + jb] : 0.0;
+
+    if (OP != 1) {  // forward substitution with the lower triangle: k ascending
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        double xk[JB];
+        ts_divide<JB>(xk, sv[k >> 2], qbase | (k & 3), mine[ts_idx<false>(k, k)], mine[136 + k]);
+#pragma unroll
+        for (int s = k >> 2; s < 4; s++) {
+          const int i = t + 4 * s;
+          const double tik = mine[ts_idx<false>(max(i, k), k)];
+#pragma unroll
+          for (int jb = 0; jb < JB; jb++) {
+            if (i > k) sv[s][jb] = sub_rn(sv[s][jb], mul_rn(tik, xk[jb]));
+            else if (i == k) sv[s][jb] = xk[jb];
+          }
+        }
+      }
+    }
+    if (OP != 0) {  // backward substitution, k descending: op 1 with the upper triangle U_ik, op 2 with L^T (t_ik = L_ki)
+#pragma unroll
+      for (int k = N - 1; k >= 0; k--) {
+        double xk[JB];
+        ts_divide<JB>(xk, sv[k >> 2], qbase | (k & 3), mine[ts_idx<UPPER>(k, k)], mine[136 + k]);
+#pragma unroll
+        for (int s = 0; s <= (k >> 2); s++) {
+          const int i = t + 4 * s;
+          const double tik = UPPER ? mine[ts_idx<true>(min(i, k), k)] : mine[ts_idx<false>(k, min(i, k))];
+#pragma unroll
+          for (int jb = 0; jb < JB; jb++) {
+            if (i < k) sv[s][jb] = sub_rn(sv[s][jb], mul_rn(tik, xk[jb]));
+            else if (i == k) sv[s][jb] = xk[jb];
+          }
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++)
+          if (j0 + jb < J) x[(int64_t)(t + 4 * s) * J + j0 + jb] = sv[s][jb];
+    }
+  }
+}
+
+template <int OP, int JB>
+static cudaError_t launch_trisolve16_op(cudaStream_t s, const double* T, const double* Y, double* X,
+                                        int64_t batch, int J, const BatchMap& map) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(trisolve16_kernel<OP, JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTs16Smem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int64_t grid = (batch + kTs16Warps * 8 - 1) / (kTs16Warps * 8);
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  trisolve16_kernel<OP, JB><<<(unsigned)grid, kTs16Warps * 32, kTs16Smem, s>>>(T, Y, X, batch, J, map);
+  return cudaGetLastError();
+}
+
+template <int JB>
+static cudaError_t launch_trisolve16(cudaStream_t s, int op, const double* T, const double* Y, double* X,
+                                     int64_t batch, int J, const BatchMap& map) {
+  if (op == 0) return launch_trisolve16_op<0, JB>(s, T, Y, X, batch, J, map);
+  if (op == 1) return launch_trisolve16_op<1, JB>(s, T, Y, X, batch, J, map);
+  return launch_trisolve16_op<2, JB>(s, T, Y, X, batch, J, map);
+}
+
 cudaError_t launch_tri_solve(cudaStream_t s, int op, const double* T, const double* Y, double* X,
                              int64_t batch, int M, int J, const BatchMap& map) {
   if (batch <= 0) return cudaSuccess;
+  if (M == 16) {
+    if (J == 1) return launch_trisolve16<1>(s, op, T, Y, X, batch, J, map);
+    if (J == 2) return launch_trisolve16<2>(s, op, T, Y, X, batch, J, map);
+    return launch_trisolve16<4>(s, op, T, Y, X, batch, J, map);
+  }
   const int64_t threads = batch * J;
   const int64_t grid = (threads + kSolveThreads - 1) / kSolveThreads;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
