@@ -38,6 +38,8 @@ WORKLOADS = {
     "c5": ("batched nd.la.svd_jac_1sided float64 [16384,64,64]", 16384, 98816, 2016 * 1152),  # flop per sweep
     # next row 8f-1: the solve that follows C3 (one right-hand side per matrix); bytes: L read whole + y in + x out
     "s3": ("batched nd.la.cholesky_solve float64 L[262144,16,16], y[262144,16,1]", 262144, 2048 + 128 + 128, 2 * 16 * 16),
+    # next row 8f-1: least squares from C4's factors; bytes: Q, R, y in, x out
+    "l4": ("batched nd.la.qr_lstsq float64 Q[65536,64,32], R[65536,32,32], y[65536,64,1]", 65536, (2048 + 1024 + 64 + 32) * 8, 2 * 64 * 32 + 32 * 32),
     # compute-bound probe of the same matmul kernel family (north_star: matmul vs FP64 tensor-core peak)
     "g4k": ("nd.la.matmul float64 4096x4096 . 4096x4096 single matrix (compute-bound probe)", 1, 3 * 4096 * 4096 * 8, 2 * 4096 ** 3),
 }
@@ -124,7 +126,7 @@ def run_reference(args):
     nd4ref.build()
     desc, units, bpu, fpu = WORKLOADS[args.workload]
     rng = np.random.default_rng(3)
-    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24, "g4k": 1, "s3": 65536}[args.workload]
+    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24, "g4k": 1, "s3": 65536, "l4": 8192}[args.workload]
     fn, data = _ref_case(args.workload, sample, rng, nd4ref)
     for _ in range(min(args.warmup, 1)):
         fn(*data)
@@ -160,6 +162,9 @@ def _ref_case(name, n, rng, nd4ref):
         return nd4ref.cholesky_decomp, (g @ g.transpose(0, 2, 1) + 16 * np.eye(16),)
     if name == "c4":
         return nd4ref.qr_decomp, (rng.uniform(-1, 1, (n, 64, 32)),)
+    if name == "l4":
+        q, r = np.linalg.qr(rng.uniform(-1, 1, (n, 64, 32)))
+        return nd4ref.qr_lstsq, (q, r, rng.uniform(-1, 1, (n, 64, 1)))
     if name == "s3":
         g = rng.uniform(-1, 1, (n, 16, 16))
         return nd4ref.cholesky_solve, (np.linalg.cholesky(g @ g.transpose(0, 2, 1) + 16 * np.eye(16)), rng.uniform(-1, 1, (n, 16, 1)))
@@ -195,6 +200,11 @@ class DeviceCase:
             del gmat
             self.b = u(units, 16, 1)
             self.out = [torch.empty(units, 16, 1, **f64)]
+        elif name == "l4":
+            self.a, self.r = torch.linalg.qr(u(units, 64, 32))
+            self.a, self.r = self.a.contiguous(), self.r.contiguous()
+            self.b = u(units, 64, 1)
+            self.out = [torch.empty(units, 32, 1, **f64)]
         elif name == "c4":
             self.a = u(units, 64, 32)
             self.out = [torch.empty(units, 64, 32, **f64), torch.empty(units, 32, 32, **f64)]
@@ -230,6 +240,8 @@ class DeviceCase:
             rc = L.nd4b_dev_cholesky_f64(d, s, p(self.a), p(self.out[0]), self.units, 16, p(self.info))
         elif self.name == "s3":
             rc = L.nd4b_dev_tri_solve_f64(d, s, 2, p(self.a), 256, p(self.b), 16, p(self.out[0]), self.units, 16, 1)
+        elif self.name == "l4":
+            rc = L.nd4b_dev_qr_lstsq_f64(d, s, p(self.a), p(self.r), p(self.b), p(self.out[0]), self.units, 64, 32, 32, 1)
         elif self.name == "c4":
             rc = L.nd4b_dev_qr_f64(d, s, p(self.a), p(self.out[0]), p(self.out[1]), self.units, 64, 32, None, 0)
         else:
@@ -280,6 +292,12 @@ def host_case(name, nd, units):
         s, l = pinned((units, 16, 16), g @ g.transpose(0, 2, 1) + 16 * np.eye(16)), pinned((units, 16, 16))
         bad = C.c_int64(0)
         return (lambda: L.nd4b_cholesky_f64(p(s), p(l), units, 16, C.byref(bad))), s.numel() * 8, l.numel() * 8, (s, l)
+    if name == "l4":
+        qq, rr = np.linalg.qr(rng.uniform(-1, 1, (units, 64, 32)))
+        q, r = pinned((units, 64, 32), qq), pinned((units, 32, 32), rr)
+        y, x = pinned((units, 64, 1), rng.uniform(-1, 1, (units, 64, 1))), pinned((units, 32, 1))
+        return ((lambda: L.nd4b_qr_lstsq_f64(p(q), p(r), p(y), p(x), units, 64, 32, 32, 1)), (q.numel() + r.numel() + y.numel()) * 8,
+                x.numel() * 8, (q, r, y, x))
     if name == "s3":
         g = rng.uniform(-1, 1, (units, 16, 16))
         l = pinned((units, 16, 16), np.linalg.cholesky(g @ g.transpose(0, 2, 1) + 16 * np.eye(16)))
@@ -390,7 +408,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         kernel = {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
-                  "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel", "s3": "trisolve16_kernel"}[args.workload]
+                  "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel", "s3": "trisolve16_kernel", "l4": "qr_lstsq32_kernel"}[args.workload]
         traffic, traffic_src = NCU_TRAFFIC_BYTES.get(args.workload, (None, None))
         if args.workload in ("c1", "g4k", "c5"):
             # compute-bound configs: against the FP64 pipe — DMMA for the GEMMs, DFMA for the Jacobi SVD; both
@@ -414,7 +432,7 @@ def run_ours(args):
             "gflops": value * flop_unit / 1e9,
             "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timing": "host wall clock around the blocking C-ABI call, barrier+sync both sides, max over ranks",
-                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1", "s3": "tri_solve"}[args.workload]},
+                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1", "s3": "tri_solve", "l4": "qr_lstsq"}[args.workload]},
             "gpu_launches": args.steps + int(e2e_launches),
             "roofline": roofline,
             "clocks": clocks,
@@ -434,7 +452,7 @@ def run_ours(args):
     # ---------------- the other BASELINE configs, kernel-only, short ----------------
     if args.workload == "c2" and not args.no_others:
         others = {}
-        for name in ("c1", "g4k", "c3", "s3", "c4", "c5"):
+        for name in ("c1", "g4k", "c3", "s3", "c4", "l4", "c5"):
             d2, u2, b2, f2 = WORKLOADS[name]
             c2 = DeviceCase(name, torch, lib, local, u2)
             barrier()
@@ -460,7 +478,7 @@ def run_ours(args):
         import numpy as np
         from oracle import nd4ref
         nd4ref.build()
-        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96, "g4k": 1, "s3": 262144}[args.workload]
+        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96, "g4k": 1, "s3": 262144, "l4": 16384}[args.workload]
         fn, data = _ref_case(args.workload, sample, np.random.default_rng(3), nd4ref)
         reps, t0 = 0, time.perf_counter()
         while True:

@@ -115,6 +115,14 @@ int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, 
  * coordinates in an orthonormal basis of range(A)'s complement: only their norms are basis independent. */
 int nd4b_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY, int64_t batch, int M, int N, int L);
 
+/* ---- nd.la.qr_lstsq — src/la/qr.js:186-273, fused for thin factors ----------------------------------------------- */
+
+/* x = argmin |Q R x - y| from the factors of qr_decomp: X[batch,I,J] = R[:L,:L]^-1 (Q[:, :L]^T Y), L = min(M,I), rows L..I-1
+ * zero — Q[batch,N,M], R[batch,M,I], Y[batch,N,J], all with the same leading batch (the shim composes matmul2 and
+ * triu_solve for broadcast operands and for factors with more than 32 columns).  Bit-identical with the reference: the
+ * products of Q^T y are summed in its order (k ascending, unfused), the back substitution is _triu_solve's (tri.js:73-98). */
+int nd4b_qr_lstsq_f64(const double* Q, const double* R, const double* Y, double* X, int64_t batch, int N, int M, int I, int J);
+
 /* ---- nd.la.svd_jac_1sided — contract of the svd_jac_* family, src/la/svd_jac_2sided.js:30-144,
  *      ordering/sign rules src/la/_svd_jac_utils.js:123-188, shapes src/help.js:2321-2337 ------- */
 
@@ -150,6 +158,8 @@ int nd4b_dev_qr_f64(int device, void* stream, const double* A, double* Q, double
 /* op as in nd4b_tri_solve_f64; T[m*t_stride] is M x M, Y[m*y_stride] is M x J (strides in elements, 0 broadcasts), X[batch,M,J]. */
 int nd4b_dev_tri_solve_f64(int device, void* stream, int op, const double* T, int64_t t_stride, const double* Y, int64_t y_stride,
                            double* X, int64_t batch, int M, int J);
+int nd4b_dev_qr_lstsq_f64(int device, void* stream, const double* Q, const double* R, const double* Y, double* X,
+                          int64_t batch, int N, int M, int I, int J);
 int nd4b_dev_qr_inplace_f64(int device, void* stream, const double* A, const double* Y, double* R, double* QtY,
                             int64_t batch, int M, int N, int L);
 /* sweeps (device int32, may be NULL): atomicMax of sweeps used.  workspace as reported below. */

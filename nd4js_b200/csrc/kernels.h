@@ -30,6 +30,10 @@ cudaError_t launch_cholesky(cudaStream_t s, const double* S, double* L, int64_t 
 cudaError_t launch_tri_solve(cudaStream_t s, int op, const double* T, const double* Y, double* X,
                              int64_t batch, int M, int J, const BatchMap& map);
 
+// qr_lstsq for thin factors (M, I <= 32), same batch for Q[N,M], R[M,I], Y[N,J]; X[I,J]; bit-exact with the reference
+cudaError_t launch_qr_lstsq(cudaStream_t s, const double* Q, const double* R, const double* Y, double* X,
+                            int64_t batch, int N, int M, int I, int J);
+
 size_t qr_workspace_bytes(int64_t batch, int rows, int cols);
 cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols,
                       double* work, size_t work_bytes);

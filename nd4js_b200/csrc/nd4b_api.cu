@@ -57,15 +57,17 @@ const char* ref_message(int code) {
   } while (0)
 
 constexpr int kSlots = 3;     // pipeline depth per device: chunk c runs on slot c % kSlots
-constexpr int kMaxBuf = 6;    // device buffers per slot: up to 2 inputs, 3 outputs, 1 workspace
+constexpr int kMaxIn = 3, kMaxOut = 3;
+constexpr int kOutBase = kMaxIn, kWorkBuf = kMaxIn + kMaxOut;
+constexpr int kMaxBuf = kWorkBuf + 1;  // device buffers per slot: up to 3 inputs, 3 outputs, 1 workspace
 
 struct Slot {
   cudaStream_t stream = nullptr;
   void* buf[kMaxBuf] = {nullptr};
   size_t cap[kMaxBuf] = {0};
-  // pinned staging ring for pageable caller memory: [0..1] inputs, [2..4] outputs
-  void* pin[5] = {nullptr};
-  size_t pin_cap[5] = {0};
+  // pinned staging ring for pageable caller memory: [0..2] inputs, [3..5] outputs
+  void* pin[kWorkBuf] = {nullptr};
+  size_t pin_cap[kWorkBuf] = {0};
   // outputs of the chunk in flight on this slot that still have to be copied from pin[] to the caller
   struct Pending { double* dst; const void* src; size_t bytes; } pending[3];
   int n_pending = 0;
@@ -281,7 +283,7 @@ struct Stream1 {           // one streamed array: `elems` doubles per unit
 struct ChunkArgs {
   Device* dev;
   cudaStream_t stream;
-  const double* in[2];
+  const double* in[kMaxIn];
   double* out[3];
   double* work;
   size_t work_bytes;
@@ -354,24 +356,24 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
       }
       for (size_t i = 0; i < outs.size(); i++) {
         const size_t bytes = (size_t)cnt * outs[i].elems * 8;
-        if (int rc = ensure(slot, 2 + (int)i, bytes)) return rc;
-        a.out[i] = static_cast<double*>(slot.buf[2 + i]);
+        if (int rc = ensure(slot, kOutBase + (int)i, bytes)) return rc;
+        a.out[i] = static_cast<double*>(slot.buf[kOutBase + i]);
       }
       a.work = nullptr;
       a.work_bytes = 0;
       if (work_bytes_per_unit) {
         a.work_bytes = work_bytes_per_unit * (size_t)cnt;
-        if (int rc = ensure(slot, 5, a.work_bytes)) return rc;
-        a.work = static_cast<double*>(slot.buf[5]);
+        if (int rc = ensure(slot, kWorkBuf, a.work_bytes)) return rc;
+        a.work = static_cast<double*>(slot.buf[kWorkBuf]);
       }
       if (int rc = launch(a)) return rc;
       for (size_t i = 0; i < outs.size(); i++) {
         const size_t bytes = (size_t)cnt * outs[i].elems * 8;
         double* dst = outs[i].out + sh.next * outs[i].elems;
         if (!out_pinned[i]) {
-          if (int rc = ensure_pinned(slot, 2 + (int)i, bytes)) return rc;
-          CU(cudaMemcpyAsync(slot.pin[2 + i], a.out[i], bytes, cudaMemcpyDeviceToHost, slot.stream));
-          slot.pending[slot.n_pending++] = {dst, slot.pin[2 + i], bytes};
+          if (int rc = ensure_pinned(slot, kOutBase + (int)i, bytes)) return rc;
+          CU(cudaMemcpyAsync(slot.pin[kOutBase + i], a.out[i], bytes, cudaMemcpyDeviceToHost, slot.stream));
+          slot.pending[slot.n_pending++] = {dst, slot.pin[kOutBase + i], bytes};
           ctx->staged += bytes;
         } else {
           CU(cudaMemcpyAsync(dst, a.out[i], bytes, cudaMemcpyDeviceToHost, slot.stream));
@@ -783,6 +785,24 @@ int nd4b_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY
                       {{nullptr, R, (int64_t)M * N}, {nullptr, QtY, (int64_t)M * L}}, 0, launch);
 }
 
+// ---- qr_lstsq (src/la/qr.js:186-273), fused form for thin factors ------------------------------
+
+int nd4b_qr_lstsq_f64(const double* Q, const double* R, const double* Y, double* X, int64_t batch, int N, int M, int I, int J) {
+  if (!Q || !R || !Y || !X) return fail(ND4B_E_ARG, "qr_lstsq: null pointer");
+  if (batch < 1 || N < 1 || M < 1 || I < 1 || J < 1) return fail(ND4B_E_ARG, "qr_lstsq: batch, N, M, I and J must be >= 1");
+  if (I > N) return fail(ND4B_E_ARG, "qr_lstsq(Q,R,y): Under-determined systems not supported. Use rrqr instead.");
+  if (M > 32 || I > 32) return fail(ND4B_E_ARG, "qr_lstsq: the fused kernel takes factors with at most 32 columns; compose matmul2 and triu_solve");
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  auto launch = [&](const ChunkArgs& a) -> int {
+    return check_cuda_launch(nd4b::launch_qr_lstsq(a.stream, a.in[0], a.in[1], a.in[2], a.out[0], a.count, N, M, I, J), ctx);
+  };
+  return run_pipeline(ctx, batch, {{Q, nullptr, (int64_t)N * M}, {R, nullptr, (int64_t)M * I}, {Y, nullptr, (int64_t)N * J}},
+                      {{nullptr, X, (int64_t)I * J}}, 0, launch);
+}
+
 // ---- svd ----------------------------------------------------------------------------------------
 
 int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
@@ -956,6 +976,15 @@ int nd4b_dev_tri_solve_f64(int device, void* stream, int op, const double* T, in
   map.a_lin = t_stride;
   map.b_lin = y_stride;
   return check_cuda_launch(nd4b::launch_tri_solve((cudaStream_t)stream, op, T, Y, X, batch, M, J, map), ctx);
+}
+
+int nd4b_dev_qr_lstsq_f64(int device, void* stream, const double* Q, const double* R, const double* Y, double* X,
+                          int64_t batch, int N, int M, int I, int J) {
+  if (!Q || !R || !Y || !X || batch < 1 || N < 1 || M < 1 || I < 1 || J < 1 || M > 32 || I > 32 || I > N)
+    return fail(ND4B_E_ARG, "dev_qr_lstsq: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  return check_cuda_launch(nd4b::launch_qr_lstsq((cudaStream_t)stream, Q, R, Y, X, batch, N, M, I, J), ctx);
 }
 
 int nd4b_dev_qr_inplace_f64(int device, void* stream, const double* A, const double* Y, double* R, double* QtY,

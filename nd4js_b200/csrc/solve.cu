@@ -235,6 +235,104 @@ static cudaError_t launch_trisolve16(cudaStream_t s, int op, const double* T, co
   return launch_trisolve16_op<2, JB>(s, T, Y, X, batch, J, map);
 }
 
+// ------------------------------------------------------------------------------------------------
+// qr_lstsq (nd4js src/la/qr.js:186-273) for thin factors, fused: x = R[:L,:L]^-1 (Q[:, :L]^T y), L = min(M, I) <= 32.
+// One warp per matrix.  Lane i accumulates (Q^T y)_i over the rows of Q in the reference's order (k ascending, product and
+// sum rounded separately, starting from the zero the reference's result array is initialised with): a row of Q is one
+// coalesced 256-byte read.  R's leading block is staged in a padded shared-memory tile (stride 33: a column is
+// conflict-free) and the back substitution runs right-looking with k descending, as _triu_solve does per entry
+// (tri.js:73-98).  Bit-identical with the reference; Q, R, y are each read once, nothing but x is written.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLsWarps = 8;
+constexpr int kLsLD = 33;
+constexpr size_t kLsSmem = sizeof(double) * kLsWarps * 32 * kLsLD;
+
+template <int JB>
+__global__ void __launch_bounds__(kLsWarps * 32)
+qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, const double* __restrict__ Y,
+                  double* __restrict__ X, int64_t batch, int N, int M, int I, int J) {
+  extern __shared__ __align__(16) double ls_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m = (int64_t)blockIdx.x * kLsWarps + warp;
+  if (m >= batch) return;  // warp-uniform
+  const int L = M < I ? M : I;
+  double* rt = ls_smem + warp * 32 * kLsLD;
+  const double* q = Q + m * (int64_t)N * M;
+  const double* r = R + m * (int64_t)M * I;
+  const double* y = Y + m * (int64_t)N * J;
+  double* x = X + m * (int64_t)I * J;
+
+  for (int i = 0; i < L; i++)  // rows of R's leading block, coalesced
+    if (lane < L) rt[i * kLsLD + lane] = ldg1_stream(r + (int64_t)i * I + lane);
+  __syncwarp();
+  // reciprocal of my diagonal entry (hoisted part of the IEEE division, common.cuh)
+  const double dii = (lane < L) ? rt[lane * kLsLD + lane] : 1.0;
+  const double yii = col_recip(dii).y;
+
+#pragma unroll 1
+  for (int j0 = 0; j0 < J; j0 += JB) {
+    double s[JB];
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++) s[jb] = 0.0;
+    // Q^T y, k ascending (the unrolled body keeps 8 row reads of 256 B in flight per warp: the kernel is HBM bound)
+#pragma unroll 8
+    for (int k = 0; k < N; k++) {
+      const double qk = (lane < L) ? ldg1_stream(q + (int64_t)k * M + lane) : 0.0;
+#pragma unroll
+      for (int jb = 0; jb < JB; jb++) {
+        const double yk = (j0 + jb < J) ? __ldg(y + (int64_t)k * J + j0 + jb) : 0.0;
+        s[jb] = add_rn(s[jb], mul_rn(qk, yk));
+      }
+    }
+    for (int k = L - 1; k >= 0; k--) {  // back substitution, k descending
+      ColRecip rc;
+      rc.b = shfl(dii, k);
+      rc.y = shfl(yii, k);
+      rc.bhi = __int_as_float(__double2hiint(rc.b));
+      const double rik = rt[(lane < k ? lane : k) * kLsLD + k];
+      double num[JB], xk[JB];
+      bool ok = true;
+#pragma unroll
+      for (int jb = 0; jb < JB; jb++) {
+        num[jb] = shfl(s[jb], k);
+        xk[jb] = div_col(num[jb], rc, ok);
+      }
+      if (!ok) {
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) xk[jb] = ts_ieee_div(num[jb], rc.b);
+      }
+#pragma unroll
+      for (int jb = 0; jb < JB; jb++) {
+        if (lane < k) s[jb] = sub_rn(s[jb], mul_rn(rik, xk[jb]));
+        else if (lane == k) s[jb] = xk[jb];
+      }
+    }
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++)
+      if (j0 + jb < J && lane < I) x[(int64_t)lane * J + j0 + jb] = (lane < L) ? s[jb] : 0.0;
+  }
+}
+
+cudaError_t launch_qr_lstsq(cudaStream_t s, const double* Q, const double* R, const double* Y, double* X,
+                            int64_t batch, int N, int M, int I, int J) {
+  if (batch <= 0) return cudaSuccess;
+  if (M > 32 || I > 32) return cudaErrorInvalidValue;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(qr_lstsq32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLsSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qr_lstsq32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLsSmem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int64_t grid = (batch + kLsWarps - 1) / kLsWarps;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  if (J == 1) qr_lstsq32_kernel<1><<<(unsigned)grid, kLsWarps * 32, kLsSmem, s>>>(Q, R, Y, X, batch, N, M, I, J);
+  else qr_lstsq32_kernel<4><<<(unsigned)grid, kLsWarps * 32, kLsSmem, s>>>(Q, R, Y, X, batch, N, M, I, J);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tri_solve(cudaStream_t s, int op, const double* T, const double* Y, double* X,
                              int64_t batch, int M, int J, const BatchMap& map) {
   if (batch <= 0) return cudaSuccess;

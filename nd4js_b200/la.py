@@ -251,8 +251,9 @@ def cholesky_solve(L, y):
 
 
 def qr_lstsq(Q, R, y=None):
-    """x = argmin |Q R x - y|: Q^T y on the GPU GEMM path, then the bit-exact back substitution.
-    The reference accumulates Q^T y sequentially (qr.js:246-249); the GEMM's rounding differs by a few ulp."""
+    """x = argmin |Q R x - y| (qr.js:186-273).  Thin factors (at most 32 columns) with one common batch run in the fused,
+    bit-exact kernel (nd4b_qr_lstsq_f64); broadcast operands and wider factors are composed from matmul2 (Q^T y on the GEMM
+    path: a few ulp from the reference's sequential sum, qr.js:246-249) and the bit-exact back substitution."""
     if y is None:
         y = R
         Q, R = Q
@@ -276,6 +277,12 @@ def qr_lstsq(Q, R, y=None):
         np.broadcast_shapes(tuple(Q.shape[:-2]), tuple(R.shape[:-2]), tuple(y.shape[:-2]))
     except ValueError:
         raise ValueError("Q, R, y are not broadcast-compatible.")
+    if m <= 32 and i_ <= 32 and tuple(Q.shape[:-2]) == tuple(R.shape[:-2]) == tuple(y.shape[:-2]):
+        qd, rd, yd = _f64(Q, "qr_lstsq"), _f64(R, "qr_lstsq"), _f64(y, "qr_lstsq")
+        x_shape = np.array(tuple(Q.shape[:-2]) + (i_, j_), np.int32)
+        x = _new(x_shape)
+        _lib.check(_lib.load().nd4b_qr_lstsq_f64(_ptr(qd), _ptr(rd), _ptr(yd), _ptr(x), qd.size // (n * m), n, m, i_, j_))
+        return NDArray(x_shape, x)
     qty = matmul2(Q.T, y).numpy()                                   # [..., m, j]
     r = R.numpy()
     x_top = triu_solve(np.ascontiguousarray(r[..., :l, :l]), np.ascontiguousarray(qty[..., :l, :])).numpy()
