@@ -139,6 +139,20 @@ napi_value QrInplace(napi_env env, napi_callback_info info) {
   return undefined(env);
 }
 
+// qrLstsq(Q, R, Y, X, batch, N, M, I, J) — the fused form for thin factors with one common batch
+napi_value QrLstsq(napi_env env, napi_callback_info info) {
+  size_t argc = 9; napi_value v[9];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 q, r, y, x; int64_t batch, n, m, i, j;
+  if (argc < 9 || !get_f64(env, v[0], &q) || !get_f64(env, v[1], &r) || !get_f64(env, v[2], &y) || !get_f64(env, v[3], &x) ||
+      !get_int(env, v[4], &batch) || !get_int(env, v[5], &n) || !get_int(env, v[6], &m) || !get_int(env, v[7], &i) || !get_int(env, v[8], &j)) return nullptr;
+  if ((int64_t)q.n != batch * n * m || (int64_t)r.n != batch * m * i || (int64_t)y.n != batch * n * j || (int64_t)x.n != batch * i * j) {
+    napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
+  }
+  if (nd4b_qr_lstsq_f64(q.p, r.p, y.p, x.p, batch, (int)n, (int)m, (int)i, (int)j)) return fail(env);
+  return undefined(env);
+}
+
 // svdJac1(A, U, sv, V, batch, rows, cols) -> sweeps
 napi_value SvdJac1(napi_env env, napi_callback_info info) {
   size_t argc = 7; napi_value v[7];
@@ -219,6 +233,7 @@ napi_value RegisterAll(napi_env env, napi_value exports) {
       {"matmulPlan", nullptr, MatmulPlan, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"cholesky", nullptr, Cholesky, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"qr", nullptr, Qr, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"qrLstsq", nullptr, QrLstsq, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"qrInplace", nullptr, QrInplace, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"triSolve", nullptr, TriSolve, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"svdJac1", nullptr, SvdJac1, nullptr, nullptr, nullptr, napi_default, nullptr},

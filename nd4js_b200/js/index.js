@@ -138,6 +138,41 @@ const tril_solve = (L, Y) => triSolve(0, L, Y, 'tril_solve(L,Y): L.ndim must be 
 const triu_solve = (U, Y) => triSolve(1, U, Y, 'triu_solve(U,Y): U.ndim must be at least 2.', 'triu_solve(U,Y): Y.ndim must be at least 2.');
 const cholesky_solve = (L, y) => triSolve(2, L, y, 'L must be at least 2D.', 'y must be at least 2D.');
 
-module.exports = {matmul2, matmul, cholesky_decomp, qr_decomp, _qr_decomp_inplace, svd_jac_1sided, tril_solve, triu_solve, cholesky_solve,
+// qr_lstsq(Q,R,y) (qr.js:186-273): fused bit-exact kernel for thin factors with one common batch, otherwise Q^T y on the GEMM
+// path followed by the bit-exact back substitution
+function qr_lstsq(Q, R, y) {
+  if (y === undefined) { y = R; [Q, R] = Q; }
+  Q = asarray(Q); if (Q.ndim < 2) throw new Error('qr_lstsq(Q,R,y): Q.ndim must be at least 2.');
+  R = asarray(R); if (R.ndim < 2) throw new Error('qr_lstsq(Q,R,y): R.ndim must be at least 2.');
+  y = asarray(y); if (y.ndim < 2) throw new Error('qr_lstsq(Q,R,y): y.ndim must be at least 2.');
+  const [N, M] = Q.shape.slice(-2), I = R.shape[R.ndim - 1], J = y.shape[y.ndim - 1], L = Math.min(M, I);
+  if (N !== y.shape[y.ndim - 2]) throw new Error("qr_lstsq(Q,R,y): Q and y don't match.");
+  if (M !== R.shape[R.ndim - 2]) throw new Error("qr_lstsq(Q,R,y): Q and R don't match.");
+  if (I > N) throw new Error('qr_lstsq(Q,R,y): Under-determined systems not supported. Use rrqr instead.');
+  const lead = a => Array.from(a.shape.slice(0, -2)).join(), sameBatch = lead(Q) === lead(R) && lead(Q) === lead(y);
+  if (M <= 32 && I <= 32 && sameBatch) {
+    const xShape = Int32Array.from([...Q.shape.slice(0, -2), I, J]), q = f64(Q, 'qr_lstsq'), batch = q.length / (N * M);
+    const X = new Float64Array(batch * I * J);
+    addon.qrLstsq(q, f64(R, 'qr_lstsq'), f64(y, 'qr_lstsq'), X, batch, N, M, I, J);
+    return new NDArray(xShape, X);
+  }
+  // composed path: Q^T y by matmul2 (broadcasting as in matmul2), its first L rows solved against R[:L,:L]; rows L..I-1 stay zero
+  const QTy = matmul2(Q.T, y);                                    // [..., M, J]
+  const nq = QTy.data.length / (M * J), top = new Float64Array(nq * L * J);
+  for (let b = 0; b < nq; b++) top.set(QTy.data.subarray(b * M * J, b * M * J + L * J), b * L * J);
+  const topShape = Int32Array.from(QTy.shape); topShape[topShape.length - 2] = L;
+  const rd = f64(R, 'qr_lstsq'), nr = rd.length / (M * I), Rl = new Float64Array(nr * L * L);
+  for (let b = 0; b < nr; b++)
+    for (let i = 0; i < L; i++) Rl.set(rd.subarray(b * M * I + i * I, b * M * I + i * I + L), b * L * L + i * L);
+  const rlShape = Int32Array.from(R.shape); rlShape[rlShape.length - 2] = L; rlShape[rlShape.length - 1] = L;
+  const x = triu_solve(new NDArray(rlShape, Rl), new NDArray(topShape, top));   // [..., L, J]
+  if (L === I) return x;
+  const xShape = Int32Array.from(x.shape); xShape[xShape.length - 2] = I;
+  const X = new Float64Array(xShape.reduce((p, q) => p * q, 1));
+  for (let b = 0; b * I * J < X.length; b++) X.set(x.data.subarray(b * L * J, (b + 1) * L * J), b * I * J);
+  return new NDArray(xShape, X);
+}
+
+module.exports = {qr_lstsq, matmul2, matmul, cholesky_decomp, qr_decomp, _qr_decomp_inplace, svd_jac_1sided, tril_solve, triu_solve, cholesky_solve,
                   init: d => addon.init(Int32Array.from(d || [])), stats: addon.stats,
                   pinnedFloat64Array: addon.pinnedFloat64Array};
