@@ -350,6 +350,136 @@ qr_generic_kernel(const double* __restrict__ A, double* __restrict__ Q, double* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Any shape that fits in shared memory: one CTA per matrix, W = [A | Y] (rows x (cols + ycols), odd leading dimension so
+// that a column walk is bank-conflict free) and Q (rows x L) in shared memory — the same Householder steps as the global
+// kernels above at shared-memory instead of L2 latency.  FORM_Q: qr_decomp (Q rows x L, R L x cols); otherwise
+// _qr_decomp_inplace (R rows x cols, Q^T Y rows x ycols).  Shapes that do not fit keep the global-memory kernels.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int qr_smem_ld(int n) { return n | 1; }
+inline size_t qr_smem_bytes(int rows, int cols, int ycols, bool form_q) {
+  const int L = rows < cols ? rows : cols;
+  return sizeof(double) * ((size_t)rows * qr_smem_ld(cols + ycols) + (form_q ? (size_t)rows * qr_smem_ld(L) : 0) + L);
+}
+constexpr size_t kQrSmemLimit = 200 * 1024;
+
+template <bool FORM_Q>
+__global__ void __launch_bounds__(kQrGenThreads)
+qr_smem_kernel(const double* __restrict__ A, const double* __restrict__ Y, double* __restrict__ Q, double* __restrict__ R,
+               double* __restrict__ QtY, int64_t batch, int rows, int cols, int ycols) {
+  extern __shared__ __align__(16) double qr_sm[];
+  const int64_t m = blockIdx.x;
+  if (m >= batch) return;
+  const int L = rows < cols ? rows : cols;
+  const int wc = cols + ycols, ldw = qr_smem_ld(wc), ldq = qr_smem_ld(L);
+  double* W = qr_sm;
+  double* q = W + (size_t)rows * ldw;
+  double* tau = q + (FORM_Q ? (size_t)rows * ldq : 0);
+  __shared__ double red[kQrGenThreads / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kQrGenThreads / 32;
+  const double* a_in = A + m * (int64_t)rows * cols;
+
+  double amax = 0.0;
+  for (int e = tid; e < rows * cols; e += kQrGenThreads) {
+    const double x = a_in[e];
+    W[(e / cols) * ldw + e % cols] = x;
+    amax = fmax(amax, fabs(x));
+  }
+  if (ycols > 0) {
+    const double* y_in = Y + m * (int64_t)rows * ycols;
+    for (int e = tid; e < rows * ycols; e += kQrGenThreads) W[(e / ycols) * ldw + cols + e % ycols] = y_in[e];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(kFull, amax, o));
+  if (lane == 0) red[warp] = amax;
+  __syncthreads();
+  amax = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) amax = fmax(amax, red[w]);
+  const double pre = pow2_prescale(amax), post = 1.0 / pre;
+  __syncthreads();
+  if (pre != 1.0) {  // A only: Q^T Y does not depend on the scale of A
+    for (int e = tid; e < rows * cols; e += kQrGenThreads) W[(e / cols) * ldw + e % cols] *= pre;
+    __syncthreads();
+  }
+
+  for (int k = 0; k < L; k++) {
+    double part = 0.0;
+    for (int i = k + 1 + tid; i < rows; i += kQrGenThreads) {
+      const double x = W[i * ldw + k];
+      part = fma(x, x, part);
+    }
+    const double sigma = block_sum(part, red);
+    const double x0 = W[k * ldw + k];
+    const Reflector h = make_reflector(x0, sigma);
+    __syncthreads();  // everyone has read x0
+    for (int i = k + 1 + tid; i < rows; i += kQrGenThreads) W[i * ldw + k] *= h.inv_v0;
+    if (tid == 0) { W[k * ldw + k] = h.beta; tau[k] = h.tau; }
+    __syncthreads();
+    for (int j = k + 1 + warp; j < wc; j += NW) {  // trailing columns of A and all columns of Y: one warp per column
+      double w = (lane == 0) ? W[k * ldw + j] : 0.0;  // v_k = 1
+      for (int i = k + 1 + lane; i < rows; i += 32) w = fma(W[i * ldw + k], W[i * ldw + j], w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
+      const double f = h.tau * w;
+      if (lane == 0) W[k * ldw + j] -= f;
+      for (int i = k + 1 + lane; i < rows; i += 32) W[i * ldw + j] = fma(-f, W[i * ldw + k], W[i * ldw + j]);
+    }
+    __syncthreads();
+  }
+
+  if (!FORM_Q) {
+    double* r_out = R + m * (int64_t)rows * cols;
+    for (int e = tid; e < rows * cols; e += kQrGenThreads) {
+      const int i = e / cols, j = e % cols;
+      r_out[e] = (j >= i) ? W[i * ldw + j] * post : 0.0;
+    }
+    double* y_out = QtY + m * (int64_t)rows * ycols;
+    for (int e = tid; e < rows * ycols; e += kQrGenThreads) y_out[e] = W[(e / ycols) * ldw + cols + e % ycols];
+    return;
+  }
+  double* r_out = R + m * (int64_t)L * cols;
+  for (int e = tid; e < L * cols; e += kQrGenThreads) {
+    const int i = e / cols, j = e % cols;
+    r_out[e] = (j >= i) ? W[i * ldw + j] * post : 0.0;
+  }
+  // Q = H_0 ... H_{L-1} [I_L; 0], backward accumulation in shared memory
+  for (int e = tid; e < rows * L; e += kQrGenThreads) q[(e / L) * ldq + e % L] = (e / L == e % L) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int k = L - 1; k >= 0; k--) {
+    const double tk = tau[k];
+    for (int j = k + warp; j < L; j += NW) {
+      double w = (lane == 0) ? q[k * ldq + j] : 0.0;
+      for (int i = k + 1 + lane; i < rows; i += 32) w = fma(W[i * ldw + k], q[i * ldq + j], w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
+      const double f = tk * w;
+      if (lane == 0) q[k * ldq + j] -= f;
+      for (int i = k + 1 + lane; i < rows; i += 32) q[i * ldq + j] = fma(-f, W[i * ldw + k], q[i * ldq + j]);
+    }
+    __syncthreads();
+  }
+  double* q_out = Q + m * (int64_t)rows * L;
+  for (int e = tid; e < rows * L; e += kQrGenThreads) q_out[e] = q[(e / L) * ldq + e % L];
+}
+
+template <bool FORM_Q>
+static cudaError_t launch_qr_smem(cudaStream_t s, const double* A, const double* Y, double* Q, double* R, double* QtY,
+                                  int64_t batch, int rows, int cols, int ycols) {
+  const size_t bytes = qr_smem_bytes(rows, cols, ycols, FORM_Q);
+  static size_t attr_bytes[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && attr_bytes[dev] < bytes) {
+    cudaError_t e = cudaFuncSetAttribute(qr_smem_kernel<FORM_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQrSmemLimit);
+    if (e != cudaSuccess) return e;
+    attr_bytes[dev] = kQrSmemLimit;
+  }
+  qr_smem_kernel<FORM_Q><<<(unsigned)batch, kQrGenThreads, bytes, s>>>(A, Y, Q, R, QtY, batch, rows, cols, ycols);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // _qr_decomp_inplace (nd4js src/la/qr.js:147-183): A[M,N] -> R (same shape, zero below the diagonal), Y[M,L] -> Q^T Y,
 // Q never formed.  One CTA per matrix working directly in the two output buffers (L2-resident); the reflectors are
 // applied to the trailing columns of A and to all columns of Y alike (one warp per column).  Same sign convention as the
@@ -426,12 +556,14 @@ cudaError_t launch_qr_inplace(cudaStream_t s, const double* A, const double* Y, 
                               int64_t batch, int M, int N, int L) {
   if (batch <= 0) return cudaSuccess;
   if (batch > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  if (qr_smem_bytes(M, N, L, false) <= kQrSmemLimit) return launch_qr_smem<false>(s, A, Y, nullptr, R, QtY, batch, M, N, L);
   qr_inplace_kernel<<<(unsigned)batch, kQrGenThreads, 0, s>>>(A, Y, R, QtY, batch, M, N, L);
   return cudaGetLastError();
 }
 
 size_t qr_workspace_bytes(int64_t batch, int rows, int cols) {
   if (rows == 64 && cols == 32) return 0;
+  if (qr_smem_bytes(rows, cols, 0, true) <= kQrSmemLimit) return 0;  // shared-memory kernel
   const int L = rows < cols ? rows : cols;
   return sizeof(double) * (size_t)batch * ((size_t)rows * cols + L);
 }
@@ -454,6 +586,8 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
     qr64x32_kernel<kQrWarps, 2><<<(unsigned)((batch + kQrWarps - 1) / kQrWarps), kQrWarps * 32, 0, s>>>(A, Q, R, batch);
     return cudaGetLastError();
   }
+  if (batch <= 0x7fffffffLL && qr_smem_bytes(rows, cols, 0, true) <= kQrSmemLimit)
+    return launch_qr_smem<true>(s, A, nullptr, Q, R, nullptr, batch, rows, cols, 0);
   const int L = rows < cols ? rows : cols;
   const size_t need = sizeof(double) * (size_t)batch * ((size_t)rows * cols + L);
   if (work == nullptr || work_bytes < need || batch > 0x7fffffffLL) return cudaErrorInvalidValue;
