@@ -605,11 +605,13 @@ __global__ void __launch_bounds__(kSvdGenThreads)
 svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
                    int64_t batch, int rows, int cols, int* sweeps_out, int* fail_out, double* __restrict__ work,
                    unsigned long long* sweep_sum) {
+  extern __shared__ __align__(16) double svd_gen_smem[];
   const int64_t m = blockIdx.x;
   if (m >= batch) return;
   const bool wide = rows < cols;
   const int mm = wide ? cols : rows, n = wide ? rows : cols;
-  double* Gt = work + m * svd_gen_scratch_doubles(rows, cols);
+  // work == nullptr: the per-matrix scratch (G^T, V^T, sigma, permutation, flags) lives in shared memory
+  double* Gt = work ? work + m * svd_gen_scratch_doubles(rows, cols) : svd_gen_smem;
   double* Vt = Gt + (size_t)n * mm;
   double* sig = Vt + (size_t)n * n;
   int* perm = reinterpret_cast<int*>(sig + n);
@@ -748,8 +750,11 @@ void set_svd_sweep_counter(int device, unsigned long long* counter) {
   if (device >= 0 && device < 64) g_sweep_sum[device] = counter;
 }
 
+constexpr size_t kSvdGenSmemLimit = 200 * 1024;
+
 size_t svd_workspace_bytes(int64_t batch, int rows, int cols) {
   if (rows == 64 && cols == 64) return 0;
+  if (sizeof(double) * svd_gen_scratch_doubles(rows, cols) <= kSvdGenSmemLimit) return 0;  // scratch in shared memory
   return sizeof(double) * (size_t)batch * svd_gen_scratch_doubles(rows, cols);
 }
 
@@ -778,7 +783,18 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
     else svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail, ssum);
     return cudaGetLastError();
   }
-  const size_t need = svd_workspace_bytes(batch, rows, cols);
+  const size_t per_matrix = sizeof(double) * svd_gen_scratch_doubles(rows, cols);
+  if (per_matrix <= kSvdGenSmemLimit) {  // same kernel, scratch in shared memory (L1 instead of L2 latency on every access)
+    static bool attr_done[64] = {false};
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(svd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvdGenSmemLimit);
+      if (e != cudaSuccess) return e;
+      attr_done[dev] = true;
+    }
+    svd_generic_kernel<<<(unsigned)batch, kSvdGenThreads, per_matrix, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, nullptr, ssum);
+    return cudaGetLastError();
+  }
+  const size_t need = per_matrix * (size_t)batch;
   if (work == nullptr || work_bytes < need) return cudaErrorInvalidValue;
   svd_generic_kernel<<<(unsigned)batch, kSvdGenThreads, 0, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, work, ssum);
   return cudaGetLastError();
