@@ -182,6 +182,13 @@ int nd4b_dev_svd_sweep_counter(int device, unsigned long long* counter);
  * roofline denominators that MEASURED_PEAKS.json lacks. */
 int nd4b_probe_fp64(int device, int which, int iters, int blocks, int threads, float* ms_out);
 
+/* Self-check of the kernels' branch-free IEEE helpers on `device`: draws `samples` pseudo-random doubles over all
+ * exponents (plus values at the limits of the fast-path ranges) and compares the inlined sqrt / division fast paths
+ * (csrc/common.cuh: what the bit-exact Cholesky and triangular-solve kernels execute) with the compiler's sqrt() and `/`.
+ * counts[0] = square roots that differ, counts[1] = quotients that differ (both must be 0), counts[2], counts[3] = how
+ * many samples took the fast paths. */
+int nd4b_selfcheck_ieee(int device, long long samples, unsigned long long seed, unsigned long long counts[4]);
+
 #ifdef __cplusplus
 }
 #endif

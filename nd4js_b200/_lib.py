@@ -15,7 +15,7 @@ SYMBOLS = [
     "nd4b_host_alloc", "nd4b_host_free", "nd4b_set_chunk_bytes", "nd4b_get_stats", "nd4b_reset_stats",
     "nd4b_matmul_shape", "nd4b_matmul_f64", "nd4b_cholesky_f64", "nd4b_qr_f64", "nd4b_svd_jac1_f64",
     "nd4b_dev_matmul_f64", "nd4b_dev_cholesky_f64", "nd4b_dev_qr_f64", "nd4b_dev_svd_jac1_f64",
-    "nd4b_dev_qr_workspace", "nd4b_dev_svd_workspace", "nd4b_probe_fp64", "nd4b_tri_solve_f64",
+    "nd4b_dev_qr_workspace", "nd4b_dev_svd_workspace", "nd4b_probe_fp64", "nd4b_selfcheck_ieee", "nd4b_tri_solve_f64",
     "nd4b_dev_svd_sweep_counter", "nd4b_qr_inplace_f64", "nd4b_dev_qr_inplace_f64", "nd4b_matmul_plan_f64", "nd4b_dev_tri_solve_f64", "nd4b_qr_lstsq_f64", "nd4b_dev_qr_lstsq_f64",
 ]
 
@@ -80,6 +80,7 @@ def load():
         "nd4b_dev_qr_inplace_f64": ([C.c_int, vp, dp, dp, dp, dp, i64, C.c_int, C.c_int, C.c_int], C.c_int),
         "nd4b_dev_svd_sweep_counter": ([C.c_int, vp], C.c_int),
         "nd4b_probe_fp64": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
+        "nd4b_selfcheck_ieee": ([C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_ulonglong)], C.c_int),
     }
     for name, (args, res) in sig.items():
         f = getattr(L, name)

@@ -57,5 +57,7 @@ void set_svd_sweep_counter(int device, unsigned long long* counter);
 // fp64 peak probes (tools/ and bench use them to measure the FP64 roofline denominators)
 cudaError_t launch_probe_dfma(cudaStream_t s, double* out, int iters, int blocks, int threads);
 cudaError_t launch_probe_dmma(cudaStream_t s, double* out, int iters, int blocks, int threads);
+cudaError_t launch_selfcheck(cudaStream_t s, long long per_thread, unsigned long long seed, unsigned long long* out,
+                             int blocks, int threads);
 
 }  // namespace nd4b

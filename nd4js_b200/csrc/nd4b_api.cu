@@ -1036,4 +1036,19 @@ int nd4b_probe_fp64(int device, int which, int iters, int blocks, int threads, f
   return ND4B_OK;
 }
 
+int nd4b_selfcheck_ieee(int device, long long samples, unsigned long long seed, unsigned long long counts[4]) {
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  if (samples <= 0 || !counts) return fail(ND4B_E_ARG, "nd4b_selfcheck_ieee: samples must be positive and counts non-null.");
+  unsigned long long* out;
+  CU(cudaMalloc(&out, 4 * sizeof(unsigned long long)));
+  CU(cudaMemset(out, 0, 4 * sizeof(unsigned long long)));
+  const int threads = 256, blocks = sms * 8;
+  const long long per_thread = (samples + (long long)threads * blocks - 1) / ((long long)threads * blocks);
+  CU(nd4b::launch_selfcheck(0, per_thread, seed, out, blocks, threads));
+  CU(cudaMemcpy(counts, out, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(out);
+  return ND4B_OK;
+}
+
 }  // extern "C"

@@ -140,3 +140,14 @@ def test_dev_svd_sweeps_and_sweep_counter(dev, ref):
     s = sv.cpu().numpy()
     assert np.max(np.abs(s - sref)) <= TOL * sref.max()
     assert np.max(np.abs((u.cpu().numpy() * s[:, None, :]) @ v.cpu().numpy() - a)) <= 64 * TOL
+
+
+def test_ieee_fast_path_helpers_match_the_compiler(dev):
+    """The bit-exact Cholesky / triangular-solve kernels inline nvcc's own sqrt and division fast paths (with a range
+    flag instead of a branch).  2^28 pseudo-random operands over all exponents, plus values at the range limits: every
+    result the helpers mark as valid must equal sqrt() / `/` bit for bit."""
+    counts = (C.c_ulonglong * 4)()
+    dev.ok(dev.lib.nd4b_selfcheck_ieee(0, 1 << 28, 20261018, counts))
+    bad_sqrt, bad_div, fast_sqrt, fast_div = (int(c) for c in counts)
+    assert bad_sqrt == 0 and bad_div == 0, (bad_sqrt, bad_div)
+    assert fast_sqrt > (1 << 27) and fast_div > (1 << 26), (fast_sqrt, fast_div)
