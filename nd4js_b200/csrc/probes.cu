@@ -58,6 +58,7 @@ __global__ void selfcheck_kernel(long long per_thread, unsigned long long seed, 
       xa = (xa & 0x000fffffffffffffull) | ((0x035ull + (xa >> 61)) << 52);          // 2^-970 .. 2^-963
       xb = (xb & 0x800fffffffffffffull) | ((0x7fcull + ((xb >> 61) & 3)) << 52);    // 2^1021 .. Inf/NaN
     }
+    if ((i & 31) == 7) xa &= 0x8000000000000000ull;                                   // +-0 numerators
     const double a = __longlong_as_double((long long)xa), b = __longlong_as_double((long long)xb);
     {
       bool ok = true;

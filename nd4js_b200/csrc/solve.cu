@@ -89,25 +89,46 @@ __device__ __forceinline__ constexpr int ts_idx(int i, int k) {
 
 __device__ __noinline__ double ts_ieee_div(double a, double b) { return a / b; }  // rare path, out of line
 
+__device__ __forceinline__ bool recip_range_ok(double b) {   // ColRecip::bnorm
+  return (((unsigned)__double2hiint(b) & 0x7fffffffu) - 0x01700000u) < 0x7d000000u;
+}
+
 // x_k = s_k / t_kk for JB right-hand sides: the owner's partial sums are fetched from its lane, the quotient is formed from
-// the precomputed reciprocal (bit-identical with `/` inside the fast-path ranges, else the full division)
+// the precomputed reciprocal (bit-identical with `/` inside the fast-path ranges; `ok` is cleared otherwise and the
+// caller redoes the matrix with ts16_slow_column).  No branch: the substitution is one basic block.
 template <int JB>
-__device__ __forceinline__ void ts_divide(double (&xk)[JB], const double (&sk)[JB], int src_lane, double tkk, double y2) {
+__device__ __forceinline__ void ts_divide(double (&xk)[JB], const double (&sk)[JB], int src_lane, double tkk, double y2, bool& ok) {
   ColRecip rc;
   rc.b = tkk;
   rc.y = y2;
   rc.bhi = __int_as_float(__double2hiint(tkk));
-  double num[JB];
-  bool ok = true;
+  rc.bnorm = recip_range_ok(tkk);
 #pragma unroll
-  for (int jb = 0; jb < JB; jb++) {
-    num[jb] = shfl(sk[jb], src_lane);
-    xk[jb] = div_col(num[jb], rc, ok);
+  for (int jb = 0; jb < JB; jb++) xk[jb] = div_col(shfl(sk[jb], src_lane), rc, ok);
+}
+
+// Rare path of trisolve16_kernel: one right-hand-side column of one matrix, sequentially, in the reference's own order with
+// the plain IEEE division (the sequences of tri_solve_kernel above), from the packed triangle in shared memory.
+template <int OP>
+__device__ __noinline__ void ts16_slow_column(const double* mine, const double* y, double* x, int J) {
+  constexpr int N = 16;
+  constexpr bool UPPER = (OP == 1);
+  double xs[N];
+  if (OP != 1) {
+    for (int i = 0; i < N; i++) {
+      double s = y[(int64_t)i * J];
+      for (int k = 0; k < i; k++) s = sub_rn(s, mul_rn(mine[ts_idx<false>(i, k)], xs[k]));
+      xs[i] = s / mine[ts_idx<false>(i, i)];
+    }
   }
-  if (!ok) {
-#pragma unroll
-    for (int jb = 0; jb < JB; jb++) xk[jb] = ts_ieee_div(num[jb], tkk);
+  if (OP != 0) {
+    for (int i = N; i-- > 0;) {
+      double s = (OP == 1) ? y[(int64_t)i * J] : xs[i];
+      for (int k = N; --k > i;) s = sub_rn(s, mul_rn(UPPER ? mine[ts_idx<true>(i, k)] : mine[ts_idx<false>(k, i)], xs[k]));
+      xs[i] = s / mine[ts_idx<UPPER>(i, i)];
+    }
   }
+  for (int i = 0; i < N; i++) x[(int64_t)i * J] = xs[i];
 }
 
 template <int OP, int JB>
@@ -161,6 +182,7 @@ trisolve16_kernel(const double* __restrict__ T, const double* __restrict__ Y, do
 #pragma unroll 1
   for (int j0 = 0; j0 < J; j0 += JB) {
     double sv[4][JB];
+    bool ok = true;
 #pragma unroll
     for (int s = 0; s < 4; s++)
 #pragma unroll
@@ -170,7 +192,7 @@ trisolve16_kernel(const double* __restrict__ T, const double* __restrict__ Y, do
 #pragma unroll
       for (int k = 0; k < N; k++) {
         double xk[JB];
-        ts_divide<JB>(xk, sv[k >> 2], qbase | (k & 3), mine[ts_idx<false>(k, k)], mine[136 + k]);
+        ts_divide<JB>(xk, sv[k >> 2], qbase | (k & 3), mine[ts_idx<false>(k, k)], mine[136 + k], ok);
 #pragma unroll
         for (int s = k >> 2; s < 4; s++) {
           const int i = t + 4 * s;
@@ -187,7 +209,7 @@ trisolve16_kernel(const double* __restrict__ T, const double* __restrict__ Y, do
 #pragma unroll
       for (int k = N - 1; k >= 0; k--) {
         double xk[JB];
-        ts_divide<JB>(xk, sv[k >> 2], qbase | (k & 3), mine[ts_idx<UPPER>(k, k)], mine[136 + k]);
+        ts_divide<JB>(xk, sv[k >> 2], qbase | (k & 3), mine[ts_idx<UPPER>(k, k)], mine[136 + k], ok);
 #pragma unroll
         for (int s = 0; s <= (k >> 2); s++) {
           const int i = t + 4 * s;
@@ -200,12 +222,17 @@ trisolve16_kernel(const double* __restrict__ T, const double* __restrict__ Y, do
         }
       }
     }
-    if (valid) {
+    int bad = ok ? 0 : 1;   // quad-uniform already (the numerators are broadcasts), made explicit
+    bad |= __shfl_xor_sync(kFull, bad, 1);
+    bad |= __shfl_xor_sync(kFull, bad, 2);
+    if (valid && !bad) {
 #pragma unroll
       for (int s = 0; s < 4; s++)
 #pragma unroll
         for (int jb = 0; jb < JB; jb++)
           if (j0 + jb < J) x[(int64_t)(t + 4 * s) * J + j0 + jb] = sv[s][jb];
+    } else if (valid && t == 0) {
+      for (int jb = 0; jb < JB && j0 + jb < J; jb++) ts16_slow_column<OP>(mine, y + j0 + jb, x + j0 + jb, J);
     }
   }
 }
@@ -289,6 +316,7 @@ qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, co
       rc.b = shfl(dii, k);
       rc.y = shfl(yii, k);
       rc.bhi = __int_as_float(__double2hiint(rc.b));
+      rc.bnorm = recip_range_ok(rc.b);
       const double rik = rt[(lane < k ? lane : k) * kLsLD + k];
       double num[JB], xk[JB];
       bool ok = true;
