@@ -302,7 +302,7 @@ qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, co
 #pragma unroll
     for (int jb = 0; jb < JB; jb++) s[jb] = 0.0;
     // Q^T y, k ascending (the unrolled body keeps 8 row reads of 256 B in flight per warp: the kernel is HBM bound)
-#pragma unroll 8
+#pragma unroll 16
     for (int k = 0; k < N; k++) {
       const double qk = (lane < L) ? ldg1_stream(q + (int64_t)k * M + lane) : 0.0;
 #pragma unroll
