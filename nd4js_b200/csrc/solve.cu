@@ -266,16 +266,16 @@ static cudaError_t launch_trisolve16(cudaStream_t s, int op, const double* T, co
 // qr_lstsq (nd4js src/la/qr.js:186-273) for thin factors, fused: x = R[:L,:L]^-1 (Q[:, :L]^T y), L = min(M, I) <= 32.
 // One warp per matrix.  Lane i accumulates (Q^T y)_i over the rows of Q in the reference's order (k ascending, product and
 // sum rounded separately, starting from the zero the reference's result array is initialised with): a row of Q is one
-// coalesced 256-byte read.  R's leading block is staged in a padded shared-memory tile (stride 33: a column is
-// conflict-free) and the back substitution runs right-looking with k descending, as _triu_solve does per entry
+// coalesced 256-byte read.  The upper triangle of R's leading block is staged in shared memory packed by columns (4.2 KB per
+// matrix, a column is contiguous: conflict-free; 32 warps per SM) and the back substitution runs right-looking with k descending, as _triu_solve does per entry
 // (tri.js:73-98).  Bit-identical with the reference; Q, R, y are each read once, nothing but x is written.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLsWarps = 8;
-constexpr int kLsLD = 33;
-constexpr size_t kLsSmem = sizeof(double) * kLsWarps * 32 * kLsLD;
+constexpr int kLsTri = 32 * 33 / 2;   // R's leading block, upper triangle packed by columns: (i, k), i <= k, at k(k+1)/2 + i
+constexpr size_t kLsSmem = sizeof(double) * kLsWarps * kLsTri;
 
 template <int JB>
-__global__ void __launch_bounds__(kLsWarps * 32)
+__global__ void __launch_bounds__(kLsWarps * 32, JB == 1 ? 4 : 3)
 qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, const double* __restrict__ Y,
                   double* __restrict__ X, int64_t batch, int N, int M, int I, int J) {
   extern __shared__ __align__(16) double ls_smem[];
@@ -283,17 +283,17 @@ qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, co
   const int64_t m = (int64_t)blockIdx.x * kLsWarps + warp;
   if (m >= batch) return;  // warp-uniform
   const int L = M < I ? M : I;
-  double* rt = ls_smem + warp * 32 * kLsLD;
+  double* rt = ls_smem + warp * kLsTri;
   const double* q = Q + m * (int64_t)N * M;
   const double* r = R + m * (int64_t)M * I;
   const double* y = Y + m * (int64_t)N * J;
   double* x = X + m * (int64_t)I * J;
 
   for (int i = 0; i < L; i++)  // rows of R's leading block, coalesced
-    if (lane < L) rt[i * kLsLD + lane] = ldg1_stream(r + (int64_t)i * I + lane);
+    if (lane < L && lane >= i) rt[lane * (lane + 1) / 2 + i] = ldg1_stream(r + (int64_t)i * I + lane);
   __syncwarp();
   // reciprocal of my diagonal entry (hoisted part of the IEEE division, common.cuh)
-  const double dii = (lane < L) ? rt[lane * kLsLD + lane] : 1.0;
+  const double dii = (lane < L) ? rt[lane * (lane + 1) / 2 + lane] : 1.0;
   const double yii = col_recip(dii).y;
 
 #pragma unroll 1
@@ -302,7 +302,7 @@ qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, co
 #pragma unroll
     for (int jb = 0; jb < JB; jb++) s[jb] = 0.0;
     // Q^T y, k ascending (the unrolled body keeps 8 row reads of 256 B in flight per warp: the kernel is HBM bound)
-#pragma unroll 16
+#pragma unroll 8
     for (int k = 0; k < N; k++) {
       const double qk = (lane < L) ? ldg1_stream(q + (int64_t)k * M + lane) : 0.0;
 #pragma unroll
@@ -317,7 +317,7 @@ qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, co
       rc.y = shfl(yii, k);
       rc.bhi = __int_as_float(__double2hiint(rc.b));
       rc.bnorm = recip_range_ok(rc.b);
-      const double rik = rt[(lane < k ? lane : k) * kLsLD + k];
+      const double rik = rt[k * (k + 1) / 2 + (lane < k ? lane : k)];
       double num[JB], xk[JB];
       bool ok = true;
 #pragma unroll
