@@ -289,12 +289,13 @@ qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, co
   const double* y = Y + m * (int64_t)N * J;
   double* x = X + m * (int64_t)I * J;
 
-  for (int i = 0; i < L; i++)  // rows of R's leading block, coalesced
-    if (lane < L && lane >= i) rt[lane * (lane + 1) / 2 + i] = ldg1_stream(r + (int64_t)i * I + lane);
-  __syncwarp();
-  // reciprocal of my diagonal entry (hoisted part of the IEEE division, common.cuh)
-  const double dii = (lane < L) ? rt[lane * (lane + 1) / 2 + lane] : 1.0;
-  const double yii = col_recip(dii).y;
+  {  // rows of R's leading block, coalesced, asynchronously: they are not needed before the first back substitution
+    const uint32_t rt_s = (uint32_t)__cvta_generic_to_shared(rt);
+    for (int i = 0; i < L; i++)
+      if (lane < L && lane >= i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rt_s + (uint32_t)(lane * (lane + 1) / 2 + i) * 8u), "l"(r + (int64_t)i * I + lane) : "memory");
+  }
+  double dii = 1.0, yii = 1.0;
 
 #pragma unroll 1
   for (int j0 = 0; j0 < J; j0 += JB) {
@@ -310,6 +311,13 @@ qr_lstsq32_kernel(const double* __restrict__ Q, const double* __restrict__ R, co
         const double yk = (j0 + jb < J) ? __ldg(y + (int64_t)k * J + j0 + jb) : 0.0;
         s[jb] = add_rn(s[jb], mul_rn(qk, yk));
       }
+    }
+    if (j0 == 0) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      // reciprocal of my diagonal entry (hoisted part of the IEEE division, common.cuh)
+      dii = (lane < L) ? rt[lane * (lane + 1) / 2 + lane] : 1.0;
+      yii = col_recip(dii).y;
     }
     for (int k = L - 1; k >= 0; k--) {  // back substitution, k descending
       ColRecip rc;
