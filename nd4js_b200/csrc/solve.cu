@@ -132,7 +132,7 @@ __device__ __noinline__ void ts16_slow_column(const double* mine, const double* 
 }
 
 template <int OP, int JB>
-__global__ void __launch_bounds__(kTs16Warps * 32)
+__global__ void __launch_bounds__(kTs16Warps * 32, 4)
 trisolve16_kernel(const double* __restrict__ T, const double* __restrict__ Y, double* __restrict__ X,
                   int64_t batch, int J, BatchMap map) {
   constexpr int N = 16;
