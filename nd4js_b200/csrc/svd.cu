@@ -362,10 +362,10 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
       rc = fma(rc * e1, fma(0.375, e1, 0.5), rc);
     }
     const double c = hc * rc;
-    const double sn = t * c;
-    const double cc = hc, ss = sn * sn, csd = 2.0 * c * sn * d;
-    const double na_r = fmax(fma(cc, na, fma(ss, nb, -csd)), 0.0);  // |c p - s q|^2
-    const double nb_r = fmax(fma(ss, na, fma(cc, nb, csd)), 0.0);   // |s p + c q|^2
+    // norms after the annihilating rotation: |c p - s q|^2 = |p|^2 - t d,  |s p + c q|^2 = |q|^2 + t d
+    // (from (1 - t^2) d + t (|p|^2 - |q|^2) = 0); the cached norms are refreshed exactly every sweep
+    const double na_r = fmax(fma(-t, d, na), 0.0);
+    const double nb_r = fmax(fma(t, d, nb), 0.0);
     r.alpha = rot ? t * Dq * Dpi : 0.0;
     r.beta = rot ? t * Dp * Dqi : 0.0;
     Dp2 = rot ? c * Dp : Dp; Dq2 = rot ? c * Dq : Dq; Dpi2 = rot ? rc * Dpi : Dpi; Dqi2 = rot ? rc * Dqi : Dqi;
