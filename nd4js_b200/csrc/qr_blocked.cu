@@ -262,33 +262,39 @@ __device__ __forceinline__ void qb_trailing(double (&a)[4][8][2], const double* 
   }
 }
 
-// R rows 8P..8P+7 (rows with beta < 0 negated, times post) for column block I.
-template <int P, int I>
+// R rows 8P..8P+7 (rows with beta < 0 negated, times post) for column block I.  PADDED: the matrix is rows x cols inside the
+// zero-padded 64 x 32 register tile; R is L x cols (L = min(rows, cols)) with row stride cols.
+template <int P, int I, bool PADDED>
 __device__ __forceinline__ void qb_store_r(const double (&a)[4][8][2], double* __restrict__ r_out, int g, int t,
-                                           unsigned s0, unsigned s1, double post) {
+                                           unsigned s0, unsigned s1, double post, int L, int cols) {
   const int row0 = 8 * P + 2 * t, col = 8 * I + g;
   double v0, v1;
   if (I < P) { v0 = 0.0; v1 = 0.0; }
   else if (I == P) { v0 = (2 * t <= g) ? flip(a[I][P][0], s0) : 0.0; v1 = (2 * t + 1 <= g) ? flip(a[I][P][1], s1) : 0.0; }
   else { v0 = flip(a[I][P][0], s0); v1 = flip(a[I][P][1], s1); }
   if (post != 1.0) { v0 *= post; v1 *= post; }  // warp-uniform, extreme magnitudes only
-  r_out[row0 * 32 + col] = v0;
-  r_out[(row0 + 1) * 32 + col] = v1;
+  if (!PADDED) {
+    r_out[row0 * 32 + col] = v0;
+    r_out[(row0 + 1) * 32 + col] = v1;
+  } else if (col < cols) {
+    if (row0 < L) r_out[row0 * cols + col] = v0;
+    if (row0 + 1 < L) r_out[(row0 + 1) * cols + col] = v1;
+  }
 }
 
-template <int P, bool REREAD>
+template <int P, bool REREAD, bool PADDED>
 __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, double* ts,
                                            double* __restrict__ r_out, int lane, int g, int t, double post, unsigned& sgn_p,
-                                           long long& qb_tm) {
+                                           long long& qb_tm, int L, int cols) {
   double tau_q;
   qb_panel<P, REREAD>(a, vs + kXsOff, lane, g, t, tau_q, sgn_p);
   QB_MARK(2);
   const unsigned s0 = __shfl_sync(kFull, sgn_p, 4 * (2 * t)), s1 = __shfl_sync(kFull, sgn_p, 4 * (2 * t + 1));
   // R: diagonal block and the zero blocks left of it; then the head of the panel becomes the clean unit-lower V
-  if (P > 0) qb_store_r<P, 0>(a, r_out, g, t, s0, s1, post);
-  if (P > 1) qb_store_r<P, 1>(a, r_out, g, t, s0, s1, post);
-  if (P > 2) qb_store_r<P, 2>(a, r_out, g, t, s0, s1, post);
-  qb_store_r<P, P>(a, r_out, g, t, s0, s1, post);
+  if (P > 0) qb_store_r<P, 0, PADDED>(a, r_out, g, t, s0, s1, post, L, cols);
+  if (P > 1) qb_store_r<P, 1, PADDED>(a, r_out, g, t, s0, s1, post, L, cols);
+  if (P > 2) qb_store_r<P, 2, PADDED>(a, r_out, g, t, s0, s1, post, L, cols);
+  qb_store_r<P, P, PADDED>(a, r_out, g, t, s0, s1, post, L, cols);
   a[P][P][0] = (2 * t > g) ? a[P][P][0] : ((2 * t == g) ? 1.0 : 0.0);
   a[P][P][1] = (2 * t + 1 > g) ? a[P][P][1] : ((2 * t + 1 == g) ? 1.0 : 0.0);
 #pragma unroll
@@ -304,9 +310,9 @@ __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, dou
   QB_MARK(4);
   if (P < 3) {
     qb_trailing<P, P>(a, vs, g, t, TT);
-    if (P < 1) qb_store_r<P, 1>(a, r_out, g, t, s0, s1, post);
-    if (P < 2) qb_store_r<P, 2>(a, r_out, g, t, s0, s1, post);
-    qb_store_r<P, 3>(a, r_out, g, t, s0, s1, post);
+    if (P < 1) qb_store_r<P, 1, PADDED>(a, r_out, g, t, s0, s1, post, L, cols);
+    if (P < 2) qb_store_r<P, 2, PADDED>(a, r_out, g, t, s0, s1, post, L, cols);
+    qb_store_r<P, 3, PADDED>(a, r_out, g, t, s0, s1, post, L, cols);
   }
   QB_MARK(5);
 }
@@ -336,9 +342,13 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
   }
 }
 
-template <int WARPS, int MINB, bool REREAD>
+// PADDED: any rows <= 64, cols <= 32: the matrix is zero-padded into the 64 x 32 register tile on load (zero rows leave the
+// reflectors unchanged, zero columns give identity reflectors after the last real column), and only the rows x L block
+// of Q and the L x cols block of R are stored.
+template <int WARPS, int MINB, bool REREAD, bool PADDED>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch) {
+qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch,
+                       int rows, int cols) {
   extern __shared__ __align__(16) double qb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -346,12 +356,13 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   if (m >= batch) return;  // warp-uniform; the kernel has no block-level barriers
   double* vs = qb_smem + warp * kQbWarpDoubles;
   double* ts = vs + kVDoubles;
-  const double* a_in = A + m * 2048;
+  const int L = PADDED ? (rows < cols ? rows : cols) : 32;
+  const double* a_in = A + m * (PADDED ? rows * cols : 2048);
 
   long long qb_tm = clock64();
   (void)qb_tm;
   double a[4][8][2];
-  const bool bulk = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;  // kernel-uniform
+  const bool bulk = !PADDED && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;  // kernel-uniform
   if (bulk) {
     if (lane == 0) bulk_load_start(vs, a_in, 16384, vs + kMbarOff);
     __syncwarp();
@@ -363,13 +374,23 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
 #pragma unroll
         for (int i = 0; i < 4; i++) a[i][j][e] = vs[(8 * j + 2 * t + e) * 32 + 8 * i + g];
     __syncwarp();  // the landing zone becomes the V store
-  } else {
+  } else if (!PADDED) {
 #pragma unroll
     for (int j = 0; j < 8; j++)
 #pragma unroll
       for (int e = 0; e < 2; e++)
 #pragma unroll
         for (int i = 0; i < 4; i++) a[i][j][e] = ldg1_stream(a_in + (8 * j + 2 * t + e) * 32 + 8 * i + g);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int row = 8 * j + 2 * t + e, col = 8 * i + g;
+          a[i][j][e] = (row < rows && col < cols) ? ldg1_stream(a_in + row * cols + col) : 0.0;
+        }
   }
 
   // scale guard (see pow2_prescale): only the binary exponent of the largest entry matters, so the maximum is taken over
@@ -393,13 +414,13 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   }
   const double post = 1.0 / pre;
 
-  double* r_out = R + m * 1024;
+  double* r_out = R + m * (PADDED ? L * cols : 1024);
   unsigned sgn[4];
   QB_MARK(0);
-  qb_r_phase<0, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm);
-  qb_r_phase<1, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm);
-  qb_r_phase<2, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm);
-  qb_r_phase<3, REREAD>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm);
+  qb_r_phase<0, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm, L, cols);
+  qb_r_phase<1, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm, L, cols);
+  qb_r_phase<2, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm, L, cols);
+  qb_r_phase<3, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm, L, cols);
 
   qb_q_phase<3>(a, vs, ts, lane, g, t);
   qb_q_phase<2>(a, vs, ts, lane, g, t);
@@ -407,7 +428,7 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   qb_q_phase<0>(a, vs, ts, lane, g, t);
   QB_MARK(6);
 
-  double* q_out = Q + m * 2048;
+  double* q_out = Q + m * (PADDED ? rows * L : 2048);
   if (bulk) {
     __syncwarp();  // every lane is done with the V store
 #pragma unroll
@@ -419,31 +440,41 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) bulk_store(q_out, vs, 16384);
-  } else {
+  } else if (!PADDED) {
 #pragma unroll
     for (int j = 0; j < 8; j++)
 #pragma unroll
       for (int e = 0; e < 2; e++)
 #pragma unroll
         for (int i = 0; i < 4; i++) q_out[(8 * j + 2 * t + e) * 32 + 8 * i + g] = flip(a[i][j][e], sgn[i]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int row = 8 * j + 2 * t + e, col = 8 * i + g;
+          if (row < rows && col < L) q_out[row * L + col] = flip(a[i][j][e], sgn[i]);
+        }
   }
   QB_MARK(7);
 }
 
 }  // namespace
 
-template <int WARPS, int MINB, bool REREAD>
-static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch) {
+template <int WARPS, int MINB, bool REREAD, bool PADDED>
+static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
   static bool attr_set[64] = {false};
   constexpr size_t smem = sizeof(double) * kQbWarpDoubles * WARPS;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB, REREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  qr64x32_blocked_kernel<WARPS, MINB, REREAD><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(A, Q, R, batch);
+  qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(A, Q, R, batch, rows, cols);
   return cudaGetLastError();
 }
 
@@ -452,8 +483,13 @@ static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double*
 // a sub-partition with named barriers (so that no DMMA stream runs beside a panel chain) was measured slower (1.55-1.70 ms):
 // the panel chains of the locked warps then collide on the shared-memory pipe instead.
 cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int variant) {
-  if (variant == 2) return qb_launch<4, 2, false>(s, A, Q, R, batch);
-  return qb_launch<4, 3, true>(s, A, Q, R, batch);
+  if (variant == 2) return qb_launch<4, 2, false, false>(s, A, Q, R, batch, 64, 32);
+  return qb_launch<4, 3, true, false>(s, A, Q, R, batch, 64, 32);
+}
+
+// rows <= 64, cols <= 32 through the zero-padded tile: the cost of a 64 x 32 factorisation whatever the shape
+cudaError_t launch_qr_padded_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
+  return qb_launch<4, 3, true, true>(s, A, Q, R, batch, rows, cols);
 }
 
 }  // namespace nd4b
