@@ -55,7 +55,7 @@ NCU_TRAFFIC_BYTES = {
     "c2": (1.577e9, "profiles/r01_ncu_c2_final.txt"),
     "c3": (1.014e9, "profiles/r01_ncu_c3_v3.txt"),
     "c4": (2.800e9, "profiles/r01_ncu_c4_blocked.txt"),
-    "c5": (1.576e9, "profiles/r01_ncu_c5_v2.txt"),
+    "c5": (1.576e9, "profiles/r01_ncu_c5_v3.txt"),
 }
 
 

@@ -335,14 +335,42 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
   // discard the result with selects): a divergent branch here costs a reconvergence barrier in every step.
   const bool rot = have && d * d > tol2 * na * nb;
   if (__any_sync(kFull, rot)) {
-    double num = nb - na, den = 2.0 * d;
-    if (fabs(num) + fabs(den) < 1e-140) { num *= 0x1p600; den *= 0x1p600; }  // only the ratio matters; keep num^2+den^2 normal
-    // Critical path of a step: t = tan(theta) = sin(2 theta) / (1 + cos(2 theta)).  1/sqrt(S) by one cubic step from the
+    const double num = nb - na, den = 2.0 * d;
+#ifndef ND4B_SVD_T_FP64
+    // Critical path of a step: t = tan(theta) = sign * |den| / (|num| + sqrt(num^2 + den^2)).  Any t gives an exactly
+    // orthogonal rotation as long as c = 1/sqrt(1 + t^2) is formed from that same t, and the off-diagonal element left
+    // behind is only (relative error of t) * d — so t is computed in single precision (2^-22: the convergence of the
+    // sweeps is unchanged to within a quarter of a sweep on average), on the FP32 pipe and the special-function unit
+    // with 4-cycle dependent latency instead of a chain of sixteen FP64 operations.  num and den are first scaled by a
+    // power of two taken from the larger exponent (exact), so that the single-precision range is never left.
+    const int hm = max(__double2hiint(num) & 0x7ff00000, __double2hiint(den) & 0x7ff00000);
+    const double scale = __hiloint2double(max(0x7fe00000 - hm, 0x00100000), 0);
+    const float nf = (float)(num * scale), df = (float)(den * scale);   // the larger magnitude lands in [1, 2)
+    const float an = fabsf(nf), ad = fabsf(df);
+    const float Sf = fmaf(an, an, ad * ad);                              // in [1, 8)
+    float yf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(Sf));
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(fmaf(Sf, yf, an)));   // 1 / (|num| + sqrt(S)), denominator >= 1
+    const float tf = __int_as_float(__float_as_int(ad * rf) | ((__float_as_int(nf) ^ __float_as_int(df)) & 0x80000000));
+    const double t = (double)tf;
+    // c = 1/sqrt(1 + t^2) and 1/c = sqrt(1 + t^2) in full precision from the t actually used (off the critical path)
+    const double w = fma(t, t, 1.0);                                     // in [1, 2]
+    double c;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(c) : "d"(w));
+    {
+      const double e1 = fma(-w * c, c, 1.0);
+      c = fma(c * e1, fma(0.375, e1, 0.5), c);
+    }
+    const double rc = w * c;
+#else
+    double numx = num, denx = den;
+    if (fabs(numx) + fabs(denx) < 1e-140) { numx *= 0x1p600; denx *= 0x1p600; }  // only the ratio matters; keep num^2+den^2 normal
+    // FP64 variant (A/B): t = sin(2 theta) / (1 + cos(2 theta)).  1/sqrt(S) by one cubic step from the
     // hardware seed y0 (2^-22 -> ~2^-66); the reciprocal of w = 1 + cos(2 theta) in [1,2] by two Newton steps from a seed
-    // taken at the approximate w, so that the two special-function latencies overlap.  c and 1/c (needed only for the
-    // scales and norms of the NEXT step) follow off the critical path.
-    const double S = fma(num, num, den * den);
-    const double an = fabs(num), ad = fabs(den);
+    // taken at the approximate w, so that the two special-function latencies overlap.
+    const double S = fma(numx, numx, denx * denx);
+    const double an = fabs(numx), ad = fabs(denx);
     double y0, r0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(S));
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(fma(an, y0, 1.0)));
@@ -353,7 +381,7 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
     const double r1 = fma(fma(-w, r0, 1.0), r0, r0);
     const double rw = fma(fma(-w, r1, 1.0), r1, r1);         // 1 / w
     double t = s2 * rw;
-    if ((num < 0.0) != (den < 0.0)) t = -t;
+    if ((numx < 0.0) != (denx < 0.0)) t = -t;
     const double hc = 0.5 * w;                               // c^2
     double rc;                                               // 1/c, one cubic step (hc in [0.5, 1])
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(hc));
@@ -362,6 +390,7 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
       rc = fma(rc * e1, fma(0.375, e1, 0.5), rc);
     }
     const double c = hc * rc;
+#endif
     // norms after the annihilating rotation: |c p - s q|^2 = |p|^2 - t d,  |s p + c q|^2 = |q|^2 + t d
     // (from (1 - t^2) d + t (|p|^2 - |q|^2) = 0); the cached norms are refreshed exactly every sweep
     const double na_r = fmax(fma(-t, d, na), 0.0);
