@@ -20,6 +20,10 @@ def gather_shards(local, total):
         return local
     world = dist.get_world_size()
     sizes = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+    if min(sizes) == max(sizes):  # equal shards: one collective straight into the result, no staging copies
+        out = local.new_empty((total,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
     pad = max(sizes)
     buf = local.new_zeros((pad,) + tuple(local.shape[1:]))
     buf[: local.shape[0]] = local

@@ -122,8 +122,11 @@ def test_two_rank_gloo_sharding_reassembles_the_reference_result(ref, tmp_path):
         "mine = nd4ref.cholesky_decomp(s[b0:b1])\n"
         "full = gather_shards(torch.from_numpy(mine), 37)\n"
         "t = max_over_ranks(float(r + 1))\n"
+        "e0, e1 = shard_range(36, r, w)\n"
+        "even = gather_shards(torch.from_numpy(np.ascontiguousarray(s[e0:e1])), 36)   # equal shards: one all_gather_into_tensor\n"
         "if r == 0:\n"
-        "    assert (full.numpy() == nd4ref.cholesky_decomp(s)).all(); assert t == float(w); print('OK')\n"
+        "    assert (full.numpy() == nd4ref.cholesky_decomp(s)).all(); assert t == float(w)\n"
+        "    assert (even.numpy() == s[:36]).all(); print('OK')\n"
         "dist.destroy_process_group()\n" % ROOT)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
