@@ -403,6 +403,147 @@ static cudaError_t launch_tiled(cudaStream_t s, const double* A, const double* B
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiny matrices (I, K, J <= 8 and I*K + K*J + I*J <= 100: 3x3, 4x4, 6x6 * 6x1, ...): HBM-bound by a wide margin (a 4x4
+// product moves 384 B for 128 flop), and a DMMA tile would be mostly padding.  One lane per matrix, 32 matrices per warp:
+// the warp stages its 32 A and B operands through shared memory with coalesced 8-byte loads (a contiguous batch is one
+// contiguous block; broadcast operands are addressed through the odometer, lane q holding matrix q's offsets), every
+// lane then forms its product from its own padded slots (odd stride: conflict-free), C_ij accumulated with FMAs over k
+// ascending, and the results leave through shared memory as coalesced stores again.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallWarps = 4;
+
+__host__ __device__ inline int small_stride(int n) { return n | 1; }   // odd number of doubles per matrix slot
+
+// Stages `cnt` doubles of each of the warp's nmat matrices (matrix q starts at base + off_q, off_q held by lane q) into
+// padded slots with 8-byte asynchronous copies: nothing waits until the caller's cp.async.wait_all, so every load of the
+// warp's 32 operands is in flight at once (a load -> store loop through registers waits for HBM once per iteration).
+__device__ __forceinline__ void small_stage(const double* __restrict__ base, int64_t my_off, int cnt, int stride,
+                                            double* slots, int nmat, int lane) {
+  const float inv = 1.0f / (float)cnt;
+  const int total = nmat * cnt;
+  const uint32_t slots_s = (uint32_t)__cvta_generic_to_shared(slots);
+  for (int g0 = 0; g0 < total; g0 += 32) {         // warp-uniform trip count: every lane takes part in the shuffle
+    const int g = g0 + lane;
+    const bool in = g < total;
+    const int q = in ? (int)(((float)g + 0.5f) * inv) : 0, e = g - q * cnt;   // exact: g < 2048
+    const int64_t off = __shfl_sync(kFull, my_off, q);
+    if (in) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slots_s + (uint32_t)(q * stride + e) * 8u), "l"(base + off + e) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32)
+matmul_small_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                    int64_t batch, int I, int K, int J, BatchMap map) {
+  extern __shared__ __align__(16) double small_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ik = I * K, kj = K * J, ij = I * J;
+  const int sa = small_stride(ik), sb = small_stride(kj), sc = small_stride(ij);
+  double* as = small_smem + (size_t)warp * 32 * (sa + sb + sc);
+  double* bs = as + 32 * sa;
+  double* cs = bs + 32 * sb;
+  const int64_t m0 = ((int64_t)blockIdx.x * kSmallWarps + warp) * 32;
+  if (m0 >= batch) return;  // warp-uniform
+  const int nmat = (int)min((int64_t)32, batch - m0);
+  int64_t ao = 0, bo = 0;
+  if (lane < nmat) decode_batch(map, m0 + lane, ao, bo);
+  small_stage(A, ao, ik, sa, as, nmat, lane);
+  small_stage(B, bo, kj, sb, bs, nmat, lane);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
+  if (lane < nmat) {
+    const double* a = as + lane * sa;
+    const double* b = bs + lane * sb;
+    double* c = cs + lane * sc;
+    for (int i = 0; i < I; i++)
+      for (int j = 0; j < J; j++) {
+        double acc = a[i * K] * b[j];
+        for (int k = 1; k < K; k++) acc = fma(a[i * K + k], b[k * J + j], acc);
+        c[i * J + j] = acc;
+      }
+  }
+  __syncwarp();
+  double* dst = C + m0 * ij;
+  const float inv_ij = 1.0f / (float)ij;
+  for (int g = lane; g < nmat * ij; g += 32) {
+    const int q = (int)(((float)g + 0.5f) * inv_ij), e = g - q * ij;
+    dst[g] = cs[q * sc + e];
+  }
+}
+
+static cudaError_t launch_matmul_small(cudaStream_t s, const double* A, const double* B, double* C,
+                                       int64_t batch, int I, int K, int J, const BatchMap& map) {
+  const size_t smem = sizeof(double) * kSmallWarps * 32 * (size_t)(small_stride(I * K) + small_stride(K * J) + small_stride(I * J));
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(matmul_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int64_t grid = (batch + kSmallWarps * 32 - 1) / (kSmallWarps * 32);
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  matmul_small_kernel<<<(unsigned)grid, kSmallWarps * 32, smem, s>>>(A, B, C, batch, I, K, J, map);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// I, K, J <= 8 beyond the one-lane-per-matrix kernel (e.g. 8x8 . 8x8): one DMMA.8x8x4 tile per matrix and k-half, the
+// fragments loaded straight from HBM (lane 4g+t: A[g][t], A[g][t+4], B[t][g], B[t+4][g]; out-of-range entries are zeros)
+// and C stored from the accumulator fragment (C[g][2t], C[g][2t+1]).  A warp walks over its matrices kFragUnroll at a
+// time so that kFragUnroll x 4 loads per lane are in flight; for 8x8 operands every 32-byte sector fetched is used.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFragWarps = 8, kFragUnroll = 8;
+
+__global__ void __launch_bounds__(kFragWarps * 32)
+matmul_frag8_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                    int64_t batch, int I, int K, int J, BatchMap map) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t m0 = ((int64_t)blockIdx.x * kFragWarps + warp) * kFragUnroll;
+  if (m0 >= batch) return;  // warp-uniform
+  const bool a0_in = g < I && t < K, a1_in = g < I && t + 4 < K;
+  const bool b0_in = t < K && g < J, b1_in = t + 4 < K && g < J;
+  double a0[kFragUnroll], a1[kFragUnroll], b0[kFragUnroll], b1[kFragUnroll];
+#pragma unroll
+  for (int u = 0; u < kFragUnroll; u++) {
+    a0[u] = a1[u] = b0[u] = b1[u] = 0.0;
+    const int64_t m = m0 + u;
+    if (m < batch) {
+      int64_t ao, bo;
+      decode_batch(map, m, ao, bo);
+      const double* a = A + ao;
+      const double* b = B + bo;
+      if (a0_in) a0[u] = ldg1_stream(a + g * K + t);
+      if (a1_in) a1[u] = ldg1_stream(a + g * K + t + 4);
+      if (b0_in) b0[u] = ldg1_stream(b + t * J + g);
+      if (b1_in) b1[u] = ldg1_stream(b + (t + 4) * J + g);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kFragUnroll; u++) {
+    const int64_t m = m0 + u;
+    if (m < batch) {   // warp-uniform
+      double c0 = 0.0, c1 = 0.0;
+      dmma884(c0, c1, a0[u], b0[u]);
+      if (K > 4) dmma884(c0, c1, a1[u], b1[u]);
+      double* c = C + m * (int64_t)(I * J) + g * J + 2 * t;
+      if (g < I && 2 * t < J) c[0] = c0;
+      if (g < I && 2 * t + 1 < J) c[1] = c1;
+    }
+  }
+}
+
+static cudaError_t launch_matmul_frag8(cudaStream_t s, const double* A, const double* B, double* C,
+                                       int64_t batch, int I, int K, int J, const BatchMap& map) {
+  const int per_cta = kFragWarps * kFragUnroll;
+  const int64_t grid = (batch + per_cta - 1) / per_cta;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  matmul_frag8_kernel<<<(unsigned)grid, kFragWarps * 32, 0, s>>>(A, B, C, batch, I, K, J, map);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, double* C,
                           int64_t batch, int I, int K, int J, const BatchMap& map, int sm_count) {
   if (batch <= 0) return cudaSuccess;
@@ -415,6 +556,10 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     matmul32_kernel<<<(unsigned)grid, kMM32Warps * 32, 0, s>>>(A, B, C, batch, map);
     return cudaGetLastError();
+  }
+  if (I <= 8 && K <= 8 && J <= 8 && batch >= 256) {
+    if (I * K + K * J + I * J <= 100) return launch_matmul_small(s, A, B, C, batch, I, K, J, map);
+    return launch_matmul_frag8(s, A, B, C, batch, I, K, J, map);
   }
   const bool vec = aligned && str_even && (K % 2 == 0) && (J % 2 == 0) && (((int64_t)I * J) % 2 == 0);
   // Tile choice: 64x64 tiles when they still give >= 2 CTAs per SM, else 64x32 (4 warps of 16x32) to
