@@ -369,6 +369,143 @@ cudaError_t launch_qr_lstsq(cudaStream_t s, const double* Q, const double* R, co
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// 16 < M <= 64 (and M < 16 with few right-hand sides per matrix): one warp per matrix, the referenced triangle staged in
+// shared memory (odd row stride: the column walk of the right-looking update is conflict-free, a row is contiguous),
+// lane l owns rows l and l + 32 of the right-hand side.  As soon as x_k is known (owner's partial sum broadcast by a
+// shuffle, IEEE quotient through the hoisted reciprocal of div.rn's fast path, the full division outside its ranges —
+// a warp-uniform branch), every row subtracts t_ik * x_k: each entry sees the reference's own sequence (k ascending
+// forward, descending backward; product and difference rounded separately), X is bit-identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTsWarpWarps = 2;
+
+template <int OP, int R, int JB>
+__global__ void __launch_bounds__(kTsWarpWarps * 32)
+trisolve_warp_kernel(const double* __restrict__ T, const double* __restrict__ Y, double* __restrict__ X,
+                     int64_t batch, int M, int J, BatchMap map) {
+  constexpr bool UPPER = (OP == 1);
+  extern __shared__ __align__(16) double tsw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m = (int64_t)blockIdx.x * kTsWarpWarps + warp;
+  if (m >= batch) return;  // warp-uniform
+  const int ld = M | 1;
+  double* tile = tsw_smem + (size_t)warp * (M * ld + M);
+  double* rcp = tile + M * ld;
+  int64_t to, yo;
+  decode_batch2(map, m, to, yo);
+  {
+    const double* src = T + to;
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    const float inv = 1.0f / (float)M;
+    for (int e = lane; e < M * M; e += 32) {
+      const int i = (int)(((float)e + 0.5f) * inv), k = e - i * M;    // exact: e < 4096
+      if (UPPER ? (k >= i) : (k <= i))
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_s + (uint32_t)(i * ld + k) * 8u), "l"(src + e) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    for (int i = lane; i < M; i += 32) rcp[i] = col_recip(tile[i * ld + i]).y;
+    __syncwarp();
+  }
+  const double* y = Y + yo;
+  double* x = X + m * (int64_t)M * J;
+  for (int j0 = 0; j0 < J; j0 += JB) {   // JB right-hand sides share the chain of a step
+    double sv[R][JB];
+#pragma unroll
+    for (int rr = 0; rr < R; rr++)
+#pragma unroll
+      for (int jb = 0; jb < JB; jb++) {
+        const int i = lane + 32 * rr;
+        sv[rr][jb] = (i < M && j0 + jb < J) ? y[(int64_t)i * J + j0 + jb] : 0.0;
+      }
+    auto quotient = [&](int k, double (&xk)[JB]) {
+      ColRecip rc;
+      rc.b = tile[k * ld + k];
+      rc.y = rcp[k];
+      rc.bhi = __int_as_float(__double2hiint(rc.b));
+      rc.bnorm = recip_range_ok(rc.b);
+      double num[JB];
+      bool ok = true;
+#pragma unroll
+      for (int jb = 0; jb < JB; jb++) {
+        const double mine = (R > 1 && k >= 32) ? sv[R - 1][jb] : sv[0][jb];
+        num[jb] = shfl(mine, k & 31);
+        xk[jb] = div_col(num[jb], rc, ok);
+      }
+      if (!ok) {   // warp-uniform
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) xk[jb] = ts_ieee_div(num[jb], rc.b);
+      }
+    };
+    if (OP != 1) {
+      for (int k = 0; k < M; k++) {
+        double xk[JB];
+        quotient(k, xk);
+#pragma unroll
+        for (int rr = 0; rr < R; rr++) {
+          const int i = lane + 32 * rr;
+          const double tik = (i > k && i < M) ? tile[i * ld + k] : 0.0;
+#pragma unroll
+          for (int jb = 0; jb < JB; jb++) {
+            if (i > k && i < M) sv[rr][jb] = sub_rn(sv[rr][jb], mul_rn(tik, xk[jb]));
+            else if (i == k) sv[rr][jb] = xk[jb];
+          }
+        }
+      }
+    }
+    if (OP != 0) {
+      for (int k = M - 1; k >= 0; k--) {
+        double xk[JB];
+        quotient(k, xk);
+#pragma unroll
+        for (int rr = 0; rr < R; rr++) {
+          const int i = lane + 32 * rr;
+          const double tik = (i < k) ? (UPPER ? tile[i * ld + k] : tile[k * ld + i]) : 0.0;
+#pragma unroll
+          for (int jb = 0; jb < JB; jb++) {
+            if (i < k) sv[rr][jb] = sub_rn(sv[rr][jb], mul_rn(tik, xk[jb]));
+            else if (i == k) sv[rr][jb] = xk[jb];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; rr++)
+#pragma unroll
+      for (int jb = 0; jb < JB; jb++) {
+        const int i = lane + 32 * rr;
+        if (i < M && j0 + jb < J) x[(int64_t)i * J + j0 + jb] = sv[rr][jb];
+      }
+  }
+}
+
+template <int OP, int R, int JB>
+static cudaError_t launch_trisolve_warp_op(cudaStream_t s, const double* T, const double* Y, double* X,
+                                           int64_t batch, int M, int J, const BatchMap& map) {
+  const size_t smem = sizeof(double) * kTsWarpWarps * ((size_t)M * (M | 1) + M);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(trisolve_warp_kernel<OP, R, JB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(double) * kTsWarpWarps * (64 * 65 + 64)));
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int64_t grid = (batch + kTsWarpWarps - 1) / kTsWarpWarps;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  trisolve_warp_kernel<OP, R, JB><<<(unsigned)grid, kTsWarpWarps * 32, smem, s>>>(T, Y, X, batch, M, J, map);
+  return cudaGetLastError();
+}
+
+template <int R, int JB>
+static cudaError_t launch_trisolve_warp(cudaStream_t s, int op, const double* T, const double* Y, double* X,
+                                        int64_t batch, int M, int J, const BatchMap& map) {
+  if (op == 0) return launch_trisolve_warp_op<0, R, JB>(s, T, Y, X, batch, M, J, map);
+  if (op == 1) return launch_trisolve_warp_op<1, R, JB>(s, T, Y, X, batch, M, J, map);
+  return launch_trisolve_warp_op<2, R, JB>(s, T, Y, X, batch, M, J, map);
+}
+
 cudaError_t launch_tri_solve(cudaStream_t s, int op, const double* T, const double* Y, double* X,
                              int64_t batch, int M, int J, const BatchMap& map) {
   if (batch <= 0) return cudaSuccess;
@@ -377,6 +514,10 @@ cudaError_t launch_tri_solve(cudaStream_t s, int op, const double* T, const doub
     if (J == 2) return launch_trisolve16<2>(s, op, T, Y, X, batch, J, map);
     return launch_trisolve16<4>(s, op, T, Y, X, batch, J, map);
   }
+  // one warp per matrix with the triangle in shared memory; tiny systems with many right-hand sides keep the
+  // thread-per-column kernel (its X / Y accesses are coalesced over the columns)
+  if (M > 16 && M <= 32) return J == 1 ? launch_trisolve_warp<1, 1>(s, op, T, Y, X, batch, M, J, map) : launch_trisolve_warp<1, 4>(s, op, T, Y, X, batch, M, J, map);
+  if (M > 32 && M <= 64) return J == 1 ? launch_trisolve_warp<2, 1>(s, op, T, Y, X, batch, M, J, map) : launch_trisolve_warp<2, 4>(s, op, T, Y, X, batch, M, J, map);
   const int64_t threads = batch * J;
   const int64_t grid = (threads + kSolveThreads - 1) / kSolveThreads;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
