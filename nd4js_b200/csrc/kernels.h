@@ -40,6 +40,8 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
 
 // rows=64, cols=32 on the FP64 tensor pipe (qr_blocked.cu); no alignment requirement beyond 8 bytes
 cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int variant);
+cudaError_t launch_qr_inplace_blocked(cudaStream_t s, const double* A, const double* Y, double* R, double* QtY,
+                                      int64_t batch, int rows, int cols, int nrhs);
 cudaError_t launch_qr_padded_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols);
 
 // _qr_decomp_inplace: R[M,N] (zero below the diagonal) and Q^T Y [M,L] without forming Q

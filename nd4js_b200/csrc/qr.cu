@@ -556,6 +556,15 @@ cudaError_t launch_qr_inplace(cudaStream_t s, const double* A, const double* Y, 
                               int64_t batch, int M, int N, int L) {
   if (batch <= 0) return cudaSuccess;
   if (batch > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  // M <= 64, N <= 32, at most 8 right-hand sides: the register kernel's R phases plus its block reflectors applied to Y
+  // (ND4B_QR_PADDED=0 keeps the shared-memory kernel for A/B timing)
+  static int padded = -1;
+  if (padded < 0) {
+    const char* ev = getenv("ND4B_QR_PADDED");
+    padded = ev ? atoi(ev) : 1;
+  }
+  if (padded && M <= 64 && N <= 32 && L >= 1 && L <= 8 && M * N >= 128)
+    return launch_qr_inplace_blocked(s, A, Y, R, QtY, batch, M, N, L);
   if (qr_smem_bytes(M, N, L, false) <= kQrSmemLimit) return launch_qr_smem<false>(s, A, Y, nullptr, R, QtY, batch, M, N, L);
   qr_inplace_kernel<<<(unsigned)batch, kQrGenThreads, 0, s>>>(A, Y, R, QtY, batch, M, N, L);
   return cudaGetLastError();

@@ -461,6 +461,115 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   QB_MARK(7);
 }
 
+// Block reflector P applied to the right-hand-side block Y (8 columns, same register layout as a column block of A):
+// Y -= V_P (T_P^T (V_P^T Y)), i.e. Y^T -= ((Y^T V_P) T_P) V_P^T — what qb_trailing does to the column blocks right of a
+// panel, here after the factorisation, with V_P still in a[P][j >= P], its row-major copy in vs and T_P in ts.
+template <int P>
+__device__ __forceinline__ void qb_apply_y(double (&yb)[8][2], const double (&a)[4][8][2], const double* vs, const double* ts,
+                                           int g, int t) {
+  Acc W{0.0, 0.0}, W2{0.0, 0.0};
+#pragma unroll
+  for (int j = P; j < 8; j++) {
+    dmma884(W.x, W.y, yb[j][0], a[P][j][0]);
+    dmma884(W2.x, W2.y, yb[j][1], a[P][j][1]);
+  }
+  W.x += W2.x;
+  W.y += W2.y;
+  Acc TT;   // T_P^T in accumulator layout from the row-major T_P
+  TT.x = ts[64 * P + 8 * (2 * t) + g];
+  TT.y = ts[64 * P + 8 * (2 * t + 1) + g];
+  Acc Z = mm8(W, TT);
+  Z.x = -Z.x;
+  Z.y = -Z.y;
+#pragma unroll
+  for (int j = P; j < 8; j++) {
+    const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + 2 * t);
+    dmma884(yb[j][0], yb[j][1], Z.x, v.x);
+    dmma884(yb[j][0], yb[j][1], Z.y, v.y);
+  }
+}
+
+// _qr_decomp_inplace (src/la/qr.js:147-183) for M <= 64, N <= 32 and at most 8 right-hand sides: the R phases of the
+// kernel above on the zero-padded matrix, then Q^T Y = H_4^T .. H_1^T Y from the stored block reflectors — Q is never
+// formed.  R is M x N (zero rows below row min(M,N)), Q^T Y is M x L with the rows of the flipped reflectors negated
+// like the rows of R (diag(R) >= 0).
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+qr64x32_inplace_kernel(const double* __restrict__ A, const double* __restrict__ Y, double* __restrict__ R,
+                       double* __restrict__ QtY, int64_t batch, int rows, int cols, int nrhs) {
+  extern __shared__ __align__(16) double qb_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t m = (int64_t)blockIdx.x * WARPS + warp;
+  if (m >= batch) return;  // warp-uniform; the kernel has no block-level barriers
+  double* vs = qb_smem + warp * kQbWarpDoubles;
+  double* ts = vs + kVDoubles;
+  const int L = rows < cols ? rows : cols;
+  const double* a_in = A + m * (rows * cols);
+  long long qb_tm = 0;
+  (void)qb_tm;
+  double a[4][8][2];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int row = 8 * j + 2 * t + e, col = 8 * i + g;
+        a[i][j][e] = (row < rows && col < cols) ? ldg1_stream(a_in + row * cols + col) : 0.0;
+      }
+  unsigned hi = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      hi = max(hi, (unsigned)__double2hiint(a[i][j][0]) & 0x7fffffffu);
+      hi = max(hi, (unsigned)__double2hiint(a[i][j][1]) & 0x7fffffffu);
+    }
+  hi = __reduce_max_sync(kFull, hi);
+  const double pre = pow2_prescale(__hiloint2double((int)hi, 0));
+  if (pre != 1.0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) { a[i][j][0] *= pre; a[i][j][1] *= pre; }
+  }
+  const double post = 1.0 / pre;
+
+  // R is rows x cols here: the rows below min(rows, cols) are zero
+  double* r_out = R + m * (rows * cols);
+  for (int e = L * cols + lane; e < rows * cols; e += 32) r_out[e] = 0.0;
+  unsigned sgn[4];
+  qb_r_phase<0, true, true>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm, L, cols);
+  qb_r_phase<1, true, true>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm, L, cols);
+  qb_r_phase<2, true, true>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm, L, cols);
+  qb_r_phase<3, true, true>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm, L, cols);
+
+  double yb[8][2];
+  const double* y_in = Y + m * (rows * nrhs);
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int row = 8 * j + 2 * t + e;
+      yb[j][e] = (row < rows && g < nrhs) ? ldg1_stream(y_in + row * nrhs + g) : 0.0;
+    }
+  qb_apply_y<0>(yb, a, vs, ts, g, t);
+  qb_apply_y<1>(yb, a, vs, ts, g, t);
+  qb_apply_y<2>(yb, a, vs, ts, g, t);
+  qb_apply_y<3>(yb, a, vs, ts, g, t);
+  double* y_out = QtY + m * (rows * nrhs);
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int row = 8 * j + 2 * t + e;
+      double v = yb[j][e];
+      if (j < 4) v = flip(v, __shfl_sync(kFull, sgn[j < 4 ? j : 0], 4 * (2 * t + e)));   // row 8j+c belongs to reflector c of panel j
+      if (row < rows && g < nrhs) y_out[row * nrhs + g] = v;
+    }
+}
+
 }  // namespace
 
 template <int WARPS, int MINB, bool REREAD, bool PADDED>
@@ -485,6 +594,22 @@ static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double*
 cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int variant) {
   if (variant == 2) return qb_launch<4, 2, false, false>(s, A, Q, R, batch, 64, 32);
   return qb_launch<4, 3, true, false>(s, A, Q, R, batch, 64, 32);
+}
+
+// _qr_decomp_inplace for M <= 64, N <= 32, L <= 8 through the register kernel (R phases + block reflectors applied to Y)
+cudaError_t launch_qr_inplace_blocked(cudaStream_t s, const double* A, const double* Y, double* R, double* QtY,
+                                      int64_t batch, int rows, int cols, int nrhs) {
+  static bool attr_set[64] = {false};
+  constexpr size_t smem = sizeof(double) * kQbWarpDoubles * 4;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(qr64x32_inplace_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  qr64x32_inplace_kernel<4, 3><<<(unsigned)((batch + 3) / 4), 128, smem, s>>>(A, Y, R, QtY, batch, rows, cols, nrhs);
+  return cudaGetLastError();
 }
 
 // rows <= 64, cols <= 32 through the zero-padded tile: the cost of a 64 x 32 factorisation whatever the shape
