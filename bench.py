@@ -328,6 +328,26 @@ def fp64_peaks(lib, dev):
     return out
 
 
+def pin_to_gpu_numa_node(index):
+    """One process per GPU: run this rank (and the library's copy threads it creates, and the first touch of its pinned
+    staging buffers) on the CPUs next to its GPU, so that the eight PCIe streams of a box do not all cross the socket
+    interconnect.  Best effort (NVML's ideal CPU set for the device); returns the number of CPUs or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -340,6 +360,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its banner / debug lines to stdout by default; stdout carries ONE JSON line, so send them to stderr
@@ -432,7 +453,8 @@ def run_ours(args):
             "gflops": value * flop_unit / 1e9,
             "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timing": "host wall clock around the blocking C-ABI call, barrier+sync both sides, max over ranks",
-                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1", "s3": "tri_solve", "l4": "qr_lstsq"}[args.workload]},
+                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1", "s3": "tri_solve", "l4": "qr_lstsq"}[args.workload],
+                    "rank_cpus_near_gpu": numa},
             "gpu_launches": args.steps + int(e2e_launches),
             "roofline": roofline,
             "clocks": clocks,
