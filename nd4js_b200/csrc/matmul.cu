@@ -1,10 +1,13 @@
 // matmul.cu — broadcast-batched fp64 GEMM kernels (replaces matmul2_RR, nd4js src/la/matmul.js:31-74).
 //
-// Two kernels:
+// Kernels:
 //  * matmul32_kernel     : I=K=J=32, one warp per matrix triple, operands loaded straight from HBM
 //                          into DMMA fragment registers with 16-byte loads.  HBM-bound
 //                          (24 576 B and 65 536 flop per matrix, AI 2.67 flop/B).
-//  * gemm_tiled_kernel   : any I,K,J; CTA tile in padded shared memory, DMMA.8x8x4 from smem.
+//  * gemm_pipe_kernel    : large / mid-sized products; cp.async-pipelined CTA tiles, DMMA.8x8x4 from smem.
+//  * gemm_tiled_kernel   : any I,K,J (odd sizes, unaligned operands); register-staged CTA tiles.
+//  * matmul_small_kernel : tiny matrices (3x3, 4x4, ...): one lane per matrix through cp.async-staged smem.
+//  * matmul_frag8_kernel : the rest up to 8x8: DMMA fragments straight from HBM.
 // The reference accumulates each C_ij sequentially in k with separately rounded mul and add; the
 // tensor-core path accumulates with fused multiply-adds in a different k order, so results agree
 // componentwise to a few ulp of (|A||B|)_ij (tests/ state the bound), not bit for bit.

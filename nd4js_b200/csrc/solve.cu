@@ -6,6 +6,9 @@
 // difference rounded separately, then divide by the diagonal.  One thread per (matrix, rhs column) replays exactly
 // that sequence (__dmul_rn/__dsub_rn, IEEE division), so X is bit-identical to the reference's.
 // Threads of a warp take consecutive rhs columns of one matrix: X/Y accesses are coalesced, T is a broadcast read.
+// That generic kernel serves M < 16 and M > 64; trisolve16_kernel (M = 16, the solves that follow C3) and
+// trisolve_warp_kernel (16 < M <= 64) keep the triangle in shared memory, and qr_lstsq32_kernel fuses Q^T y with
+// the back substitution — all with the same per-entry sequences, i.e. bit-identical results.
 #include "common.cuh"
 #include "kernels.h"
 
