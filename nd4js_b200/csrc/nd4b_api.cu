@@ -293,6 +293,17 @@ struct ChunkArgs {
 
 // Runs `launch` over `units` independent units: contiguous shards per device, chunks per shard,
 // chunk c of a device on slot c % kSlots (H2D -> kernel -> D2H on one stream; slots overlap).
+// Chunk sizes ramp up (1/8, 1/4, 1/2 of the nominal chunk, then full chunks) and down again at the end of a shard: the
+// pipeline's exposed latency is the H2D of the first chunk plus the D2H of the last one, which at PCIe speed is
+// 5-10 % of a whole BASELINE config with 32 MiB chunks.
+static int64_t next_chunk_units(int64_t full, int chunk_index, int64_t remaining) {
+  const int64_t small = std::max<int64_t>(1, full / 8);
+  int64_t cnt = full;
+  if (chunk_index < 3) cnt = std::max<int64_t>(small, full >> (3 - chunk_index));
+  if (remaining <= 2 * cnt) cnt = std::max<int64_t>(small, (remaining + 1) / 2);
+  return std::min(cnt, remaining);
+}
+
 int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, const std::vector<Stream1>& outs,
                  size_t work_bytes_per_unit, const std::function<int(const ChunkArgs&)>& launch) {
   const int nd = (int)ctx->devs.size();
@@ -331,7 +342,7 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
       Device& dev = ctx->devs[d];
       CU(cudaSetDevice(dev.id));
       Slot& slot = dev.slots[sh.chunk % kSlots];
-      const int64_t cnt = std::min(chunk_units, sh.b1 - sh.next);
+      const int64_t cnt = next_chunk_units(chunk_units, sh.chunk, sh.b1 - sh.next);
       // the slot's device buffers are reused in stream order; its pinned ring must be drained first
       if (int rc = drain_slot(ctx, slot)) return rc;
       ChunkArgs a{};
