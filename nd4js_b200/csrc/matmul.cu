@@ -435,9 +435,13 @@ __device__ __forceinline__ void small_stage(const double* __restrict__ base, int
   }
 }
 
+// CI, CK, CJ > 0: compile-time dimensions (3x3, 4x4 products and their matrix-vector forms): the lane's product is fully
+// unrolled from registers; 0: run-time dimensions.
+template <int CI, int CK, int CJ>
 __global__ void __launch_bounds__(kSmallWarps * 32)
 matmul_small_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
-                    int64_t batch, int I, int K, int J, BatchMap map) {
+                    int64_t batch, int I_, int K_, int J_, BatchMap map) {
+  const int I = CI ? CI : I_, K = CK ? CK : K_, J = CJ ? CJ : J_;
   extern __shared__ __align__(16) double small_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ik = I * K, kj = K * J, ij = I * J;
@@ -458,12 +462,31 @@ matmul_small_kernel(const double* __restrict__ A, const double* __restrict__ B, 
     const double* a = as + lane * sa;
     const double* b = bs + lane * sb;
     double* c = cs + lane * sc;
-    for (int i = 0; i < I; i++)
-      for (int j = 0; j < J; j++) {
-        double acc = a[i * K] * b[j];
-        for (int k = 1; k < K; k++) acc = fma(a[i * K + k], b[k * J + j], acc);
-        c[i * J + j] = acc;
+    if (CI) {
+      double br[(CK ? CK : 1) * (CJ ? CJ : 1)];
+#pragma unroll
+      for (int e = 0; e < CK * CJ; e++) br[e] = b[e];
+#pragma unroll
+      for (int i = 0; i < CI; i++) {
+        double ar[CK ? CK : 1];
+#pragma unroll
+        for (int k = 0; k < CK; k++) ar[k] = a[i * CK + k];
+#pragma unroll
+        for (int j = 0; j < CJ; j++) {
+          double acc = ar[0] * br[j];
+#pragma unroll
+          for (int k = 1; k < CK; k++) acc = fma(ar[k], br[k * CJ + j], acc);
+          c[i * CJ + j] = acc;
+        }
       }
+    } else {
+      for (int i = 0; i < I; i++)
+        for (int j = 0; j < J; j++) {
+          double acc = a[i * K] * b[j];
+          for (int k = 1; k < K; k++) acc = fma(a[i * K + k], b[k * J + j], acc);
+          c[i * J + j] = acc;
+        }
+    }
   }
   __syncwarp();
   double* dst = C + m0 * ij;
@@ -474,21 +497,32 @@ matmul_small_kernel(const double* __restrict__ A, const double* __restrict__ B, 
   }
 }
 
-static cudaError_t launch_matmul_small(cudaStream_t s, const double* A, const double* B, double* C,
-                                       int64_t batch, int I, int K, int J, const BatchMap& map) {
+template <int CI, int CK, int CJ>
+static cudaError_t launch_matmul_small_t(cudaStream_t s, const double* A, const double* B, double* C,
+                                         int64_t batch, int I, int K, int J, const BatchMap& map) {
   const size_t smem = sizeof(double) * kSmallWarps * 32 * (size_t)(small_stride(I * K) + small_stride(K * J) + small_stride(I * J));
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(matmul_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(matmul_small_kernel<CI, CK, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   const int64_t grid = (batch + kSmallWarps * 32 - 1) / (kSmallWarps * 32);
   if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  matmul_small_kernel<<<(unsigned)grid, kSmallWarps * 32, smem, s>>>(A, B, C, batch, I, K, J, map);
+  matmul_small_kernel<CI, CK, CJ><<<(unsigned)grid, kSmallWarps * 32, smem, s>>>(A, B, C, batch, I, K, J, map);
   return cudaGetLastError();
+}
+
+static cudaError_t launch_matmul_small(cudaStream_t s, const double* A, const double* B, double* C,
+                                       int64_t batch, int I, int K, int J, const BatchMap& map) {
+  if (I == 4 && K == 4 && J == 4) return launch_matmul_small_t<4, 4, 4>(s, A, B, C, batch, I, K, J, map);
+  if (I == 3 && K == 3 && J == 3) return launch_matmul_small_t<3, 3, 3>(s, A, B, C, batch, I, K, J, map);
+  if (I == 2 && K == 2 && J == 2) return launch_matmul_small_t<2, 2, 2>(s, A, B, C, batch, I, K, J, map);
+  if (I == 4 && K == 4 && J == 1) return launch_matmul_small_t<4, 4, 1>(s, A, B, C, batch, I, K, J, map);
+  if (I == 3 && K == 3 && J == 1) return launch_matmul_small_t<3, 3, 1>(s, A, B, C, batch, I, K, J, map);
+  return launch_matmul_small_t<0, 0, 0>(s, A, B, C, batch, I, K, J, map);
 }
 
 // ------------------------------------------------------------------------------------------------
