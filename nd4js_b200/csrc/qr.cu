@@ -570,6 +570,131 @@ cudaError_t launch_qr_inplace(cudaStream_t s, const double* A, const double* Y, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiny matrices (rows, cols <= 8): one lane per matrix, 32 matrices per warp.  The warp's matrices (one contiguous block)
+// are staged with 8-byte cp.async into odd-stride shared-memory slots (conflict-free), every lane runs an unblocked
+// Householder QR on its own slot (reflectors stored below the diagonal, Q accumulated backwards from [I; 0], rows of R /
+// columns of Q with a negative diagonal entry negated, power-of-two prescaling against overflow of the squared norms)
+// and the results leave through the slots as coalesced stores.  A 3x3 factorisation moves 216 B: HBM bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int kQrTinyWarps = 4;
+
+__global__ void __launch_bounds__(kQrTinyWarps * 32)
+qr_tiny_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch, int rows, int cols) {
+  extern __shared__ __align__(16) double qrt_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = rows < cols ? rows : cols;
+  const int na = rows * cols, nq = rows * L, nr = L * cols;
+  const int sa = na | 1, sq = nq | 1;
+  double* as = qrt_smem + (size_t)warp * 32 * (sa + sq + 8);
+  double* qs = as + 32 * sa;
+  double* taus = qs + 32 * sq;
+  const int64_t m0 = ((int64_t)blockIdx.x * kQrTinyWarps + warp) * 32;
+  if (m0 >= batch) return;  // warp-uniform
+  const int nmat = (int)min((int64_t)32, batch - m0);
+  {
+    const double* src = A + m0 * na;
+    const uint32_t as_s = (uint32_t)__cvta_generic_to_shared(as);
+    const float inv = 1.0f / (float)na;
+    for (int g = lane; g < nmat * na; g += 32) {
+      const int q = (int)(((float)g + 0.5f) * inv), e = g - q * na;   // exact: g < 2048
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(as_s + (uint32_t)(q * sa + e) * 8u), "l"(src + g) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+  }
+  if (lane < nmat) {
+    double* a = as + lane * sa;
+    double* q = qs + lane * sq;
+    double* tau = taus + lane * 8;
+    double amax = 0.0;
+    for (int e = 0; e < na; e++) amax = fmax(amax, fabs(a[e]));
+    const double pre = pow2_prescale(amax);
+    if (pre != 1.0)
+      for (int e = 0; e < na; e++) a[e] *= pre;
+    for (int j = 0; j < L; j++) {
+      double sigma = 0.0;
+      for (int i = j + 1; i < rows; i++) sigma = fma(a[i * cols + j], a[i * cols + j], sigma);
+      const double alpha = a[j * cols + j];
+      double t = 0.0;
+      if (sigma > 0.0) {
+        const double nrm = sqrt(fma(alpha, alpha, sigma));
+        const double beta = alpha >= 0.0 ? -nrm : nrm;
+        t = (beta - alpha) / beta;
+        const double sc = 1.0 / (alpha - beta);
+        for (int i = j + 1; i < rows; i++) a[i * cols + j] *= sc;
+        a[j * cols + j] = beta;
+        for (int c = j + 1; c < cols; c++) {
+          double w = a[j * cols + c];
+          for (int i = j + 1; i < rows; i++) w = fma(a[i * cols + j], a[i * cols + c], w);
+          w *= t;
+          a[j * cols + c] -= w;
+          for (int i = j + 1; i < rows; i++) a[i * cols + c] = fma(-w, a[i * cols + j], a[i * cols + c]);
+        }
+      }
+      tau[j] = t;
+    }
+    // Q = H_0 .. H_{L-1} [I; 0], accumulated backwards
+    for (int e = 0; e < nq; e++) q[e] = 0.0;
+    for (int j = 0; j < L; j++) q[j * L + j] = 1.0;
+    for (int j = L - 1; j >= 0; j--) {
+      const double t = tau[j];
+      if (t != 0.0)
+        for (int c = j; c < L; c++) {
+          double w = q[j * L + c];
+          for (int i = j + 1; i < rows; i++) w = fma(a[i * cols + j], q[i * L + c], w);
+          w *= t;
+          q[j * L + c] -= w;
+          for (int i = j + 1; i < rows; i++) q[i * L + c] = fma(-w, a[i * cols + j], q[i * L + c]);
+        }
+    }
+    // R: exact zeros below the diagonal, diag >= 0 (row j of R and column j of Q negated together), scale undone
+    const double post = 1.0 / pre;
+    for (int j = 0; j < L; j++) {
+      const bool neg = a[j * cols + j] < 0.0;
+      for (int c = 0; c < cols; c++) {
+        double v = (c < j) ? 0.0 : a[j * cols + c];
+        if (neg && c >= j) v = -v;
+        a[j * cols + c] = (post != 1.0) ? v * post : v;
+      }
+      if (neg)
+        for (int i = 0; i < rows; i++) q[i * L + j] = -q[i * L + j];
+    }
+  }
+  __syncwarp();
+  {
+    double* qd = Q + m0 * nq;
+    const float invq = 1.0f / (float)nq;
+    for (int g = lane; g < nmat * nq; g += 32) {
+      const int q = (int)(((float)g + 0.5f) * invq), e = g - q * nq;
+      qd[g] = qs[q * sq + e];
+    }
+    double* rd = R + m0 * nr;
+    const float invr = 1.0f / (float)nr;
+    for (int g = lane; g < nmat * nr; g += 32) {
+      const int q = (int)(((float)g + 0.5f) * invr), e = g - q * nr;   // R = the first L rows of the slot (row stride cols)
+      rd[g] = as[q * sa + e];
+    }
+  }
+}
+
+static cudaError_t launch_qr_tiny(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
+  const int L = rows < cols ? rows : cols;
+  const size_t smem = sizeof(double) * kQrTinyWarps * 32 * (size_t)((rows * cols | 1) + (rows * L | 1) + 8);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(qr_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int64_t grid = (batch + kQrTinyWarps * 32 - 1) / (kQrTinyWarps * 32);
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  qr_tiny_kernel<<<(unsigned)grid, kQrTinyWarps * 32, smem, s>>>(A, Q, R, batch, rows, cols);
+  return cudaGetLastError();
+}
+
 size_t qr_workspace_bytes(int64_t batch, int rows, int cols) {
   if (rows <= 64 && cols <= 32) return 0;
   if (qr_smem_bytes(rows, cols, 0, true) <= kQrSmemLimit) return 0;  // shared-memory kernel
@@ -604,6 +729,7 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
   }
   if (padded && rows <= 64 && cols <= 32 && rows * cols >= 128 && batch <= 0x7fffffffLL)
     return launch_qr_padded_blocked(s, A, Q, R, batch, rows, cols);
+  if (padded && rows <= 8 && cols <= 8 && batch >= 64) return launch_qr_tiny(s, A, Q, R, batch, rows, cols);
   if (batch <= 0x7fffffffLL && qr_smem_bytes(rows, cols, 0, true) <= kQrSmemLimit)
     return launch_qr_smem<true>(s, A, nullptr, Q, R, nullptr, batch, rows, cols, 0);
   const int L = rows < cols ? rows : cols;
