@@ -826,6 +826,169 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   for (int l = tid; l < n; l += kSvdGenThreads) SV[m * n + l] = zero_flag[perm[l]] ? 0.0 : sig[perm[l]] * post;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiny matrices (rows, cols <= 8): one lane per matrix, 32 matrices per warp, staged with 8-byte cp.async into odd-stride
+// shared-memory slots.  Each lane runs a cyclic one-sided Jacobi on its own slot (the transpose when the matrix is wide),
+// with the threshold, the ordering and sign conventions, the zero-column completion and the exactness on diagonal input
+// of the kernels above; the results leave as coalesced stores that apply the descending order on the fly.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSvdTinyWarps = 2;
+
+__global__ void __launch_bounds__(kSvdTinyWarps * 32)
+svd_tiny_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
+                int64_t batch, int rows, int cols, int* sweeps_out, int* fail_out, unsigned long long* sweep_sum) {
+  extern __shared__ __align__(16) double svt_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool wide = rows < cols;
+  const int mm = wide ? cols : rows, n = wide ? rows : cols;   // G is mm x n (n columns of length mm), V is n x n
+  const int na = rows * cols, sg = na | 1, sv_ = (n * n) | 1, sl = sg + sv_ + 16;
+  double* slots = svt_smem + (size_t)warp * 32 * sl;
+  const int64_t m0 = ((int64_t)blockIdx.x * kSvdTinyWarps + warp) * 32;
+  if (m0 >= batch) return;  // warp-uniform
+  const int nmat = (int)min((int64_t)32, batch - m0);
+  {
+    const double* src = A + m0 * na;
+    const uint32_t base_s = (uint32_t)__cvta_generic_to_shared(slots);
+    const float inv = 1.0f / (float)na;
+    for (int g = lane; g < nmat * na; g += 32) {
+      const int q = (int)(((float)g + 0.5f) * inv), e = g - q * na;   // exact: g < 2048
+      // tall / square: G = A (row-major mm x n); wide: G = A^T, i.e. G[i][j] = A[j][i]
+      const int pos = wide ? (e % cols) * n + e / cols : e;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(base_s + (uint32_t)(q * sl + pos) * 8u), "l"(src + g) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+  }
+  int my_sweeps = 0, my_fail = 0;
+  if (lane < nmat) {
+    double* G = slots + lane * sl;
+    double* Vv = G + sg;
+    double* sig = Vv + sv_;
+    double* permd = sig + 8;
+    double amax = 0.0;
+    for (int e = 0; e < na; e++) amax = fmax(amax, fabs(G[e]));
+    const double pre = pow2_prescale(amax);
+    if (pre != 1.0)
+      for (int e = 0; e < na; e++) G[e] *= pre;
+    for (int e = 0; e < n * n; e++) Vv[e] = 0.0;
+    for (int j = 0; j < n; j++) Vv[j * n + j] = 1.0;
+    const double tol2 = ((double)mm * kEps) * ((double)mm * kEps);
+    bool converged = false;
+    while (my_sweeps < kMaxSweeps && !converged) {
+      my_sweeps++;
+      converged = true;
+      for (int p = 0; p < n - 1; p++)
+        for (int q = p + 1; q < n; q++) {
+          double a = 0.0, b = 0.0, d = 0.0;
+          for (int i = 0; i < mm; i++) {
+            const double x = G[i * n + p], y = G[i * n + q];
+            a = fma(x, x, a); b = fma(y, y, b); d = fma(x, y, d);
+          }
+          if (!(d * d > tol2 * a * b)) continue;
+          converged = false;
+          const double zeta = (b - a) / (2.0 * d);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+          const double c = 1.0 / sqrt(fma(t, t, 1.0)), sn = c * t;
+          for (int i = 0; i < mm; i++) {
+            const double x = G[i * n + p], y = G[i * n + q];
+            G[i * n + p] = c * x - sn * y;
+            G[i * n + q] = sn * x + c * y;
+          }
+          for (int i = 0; i < n; i++) {
+            const double x = Vv[i * n + p], y = Vv[i * n + q];
+            Vv[i * n + p] = c * x - sn * y;
+            Vv[i * n + q] = sn * x + c * y;
+          }
+        }
+    }
+    if (!converged) my_fail = 1;
+    // singular values, stable descending order, zero detection
+    double smax = 0.0;
+    for (int j = 0; j < n; j++) {
+      double a = 0.0;
+      for (int i = 0; i < mm; i++) a = fma(G[i * n + j], G[i * n + j], a);
+      sig[j] = sqrt(a);
+      smax = fmax(smax, sig[j]);
+    }
+    unsigned zero_mask = 0, done_mask = 0;
+    for (int j = 0; j < n; j++) {
+      int rank = 0;
+      for (int k = 0; k < n; k++) rank += (sig[k] > sig[j]) || (sig[k] == sig[j] && k < j);
+      permd[rank] = (double)j;
+      if (!(sig[j] > smax * 1e-290) || !(sig[j] >= DBL_MIN)) zero_mask |= 1u << j;
+    }
+    for (int j = 0; j < n; j++)
+      if (!((zero_mask >> j) & 1)) {
+        const double sj = sig[j];
+        for (int i = 0; i < mm; i++) G[i * n + j] /= sj;
+      }
+    // zero columns -> completed to an orthonormal set (as complete_basis_warp does)
+    for (int z = 0; z < n; z++) {
+      if (!((zero_mask >> z) & 1)) continue;
+      double best = DBL_MAX;
+      int best_i = 0;
+      for (int i = 0; i < mm; i++) {
+        double rn = 0.0;
+        for (int k = 0; k < n; k++)
+          if (!((zero_mask >> k) & 1) || ((done_mask >> k) & 1)) rn = fma(G[i * n + k], G[i * n + k], rn);
+        if (rn < best) { best = rn; best_i = i; }
+      }
+      for (int i = 0; i < mm; i++) G[i * n + z] = (i == best_i) ? 1.0 : 0.0;
+      for (int pass = 0; pass < 2; pass++)
+        for (int k = 0; k < n; k++) {
+          if (k == z || (((zero_mask >> k) & 1) && !((done_mask >> k) & 1))) continue;
+          double dot = 0.0;
+          for (int i = 0; i < mm; i++) dot = fma(G[i * n + k], G[i * n + z], dot);
+          if (dot != 0.0)
+            for (int i = 0; i < mm; i++) G[i * n + z] = fma(-dot, G[i * n + k], G[i * n + z]);
+        }
+      double nn = 0.0;
+      for (int i = 0; i < mm; i++) nn = fma(G[i * n + z], G[i * n + z], nn);
+      if (nn != 1.0) {
+        const double inv = 1.0 / sqrt(nn);
+        for (int i = 0; i < mm; i++) G[i * n + z] *= inv;
+      }
+      done_mask |= 1u << z;
+    }
+    const double post = 1.0 / pre;
+    for (int j = 0; j < n; j++) sig[j] = ((zero_mask >> j) & 1) ? 0.0 : sig[j] * post;
+  }
+  __syncwarp();
+  {  // coalesced stores; n = L.  tall / square: U = G[:, perm], V_out[l][j] = V[j][perm[l]];  wide: U = V[:, perm], V_out[l][j] = G[j][perm[l]]
+    const int nu = rows * n, nv = n * cols;
+    double* ud = U + m0 * nu;
+    const float invu = 1.0f / (float)nu;
+    for (int g = lane; g < nmat * nu; g += 32) {
+      const int q = (int)(((float)g + 0.5f) * invu), e = g - q * nu, i = e / n, l = e - i * n;
+      const double* S0 = slots + q * sl;
+      const int pl = (int)S0[sg + sv_ + 8 + l];
+      ud[g] = wide ? S0[sg + i * n + pl] : S0[i * n + pl];
+    }
+    double* vd = V + m0 * nv;
+    const float invv = 1.0f / (float)nv;
+    for (int g = lane; g < nmat * nv; g += 32) {
+      const int q = (int)(((float)g + 0.5f) * invv), e = g - q * nv, l = e / cols, j = e - l * cols;
+      const double* S0 = slots + q * sl;
+      const int pl = (int)S0[sg + sv_ + 8 + l];
+      vd[g] = wide ? S0[j * n + pl] : S0[sg + j * n + pl];
+    }
+    double* sd = SV + m0 * n;
+    for (int g = lane; g < nmat * n; g += 32) {
+      const int q = g / n, l = g - q * n;
+      const double* S0 = slots + q * sl;
+      sd[g] = S0[sg + sv_ + (int)S0[sg + sv_ + 8 + l]];
+    }
+  }
+  const int wmax = __reduce_max_sync(kFull, my_sweeps);
+  const int wsum = __reduce_add_sync(kFull, my_sweeps);
+  const int wfail = __reduce_max_sync(kFull, my_fail);
+  if (lane == 0) {
+    if (sweeps_out) atomicMax(sweeps_out, wmax);
+    if (sweep_sum) atomicAdd(sweep_sum, (unsigned long long)wsum);
+    if (wfail && fail_out) atomicExch(fail_out, 1);
+  }
+}
+
 // Diagnostic: device counter that every following SVD launch on `device` adds its per-matrix sweep counts to (nullptr: off).
 static unsigned long long* g_sweep_sum[64] = {nullptr};
 void set_svd_sweep_counter(int device, unsigned long long* counter) {
@@ -854,6 +1017,19 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
   if (padded < 0) {
     const char* ev = getenv("ND4B_SVD_PADDED");
     padded = ev ? atoi(ev) : 1;
+  }
+  if (padded && rows <= 8 && cols <= 8 && batch >= 64) {
+    const int nn = rows < cols ? rows : cols;
+    const size_t smem = sizeof(double) * kSvdTinyWarps * 32 * (size_t)((rows * cols | 1) + (nn * nn | 1) + 16);
+    static bool tattr_set[64] = {false};
+    if (dev >= 0 && dev < 64 && !tattr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(svd_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e != cudaSuccess) return e;
+      tattr_set[dev] = true;
+    }
+    const int64_t grid = (batch + kSvdTinyWarps * 32 - 1) / (kSvdTinyWarps * 32);
+    svd_tiny_kernel<<<(unsigned)grid, kSvdTinyWarps * 32, smem, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, ssum);
+    return cudaGetLastError();
   }
   if (padded && rows <= 64 && cols <= 64 && !(rows == 64 && cols == 64) && (rows > 24 || cols > 24) && rows * cols >= 512) {
     static bool pattr_set[64] = {false};
