@@ -683,7 +683,10 @@ __host__ __device__ inline size_t svd_gen_scratch_doubles(int rows, int cols) {
   return n * mm + n * n + n + (3 * n + 1) / 2 + 1;
 }
 
-__global__ void __launch_bounds__(kSvdGenThreads)
+// T threads per matrix; a pair of columns is rotated by a group of LPP lanes (32, or 16 / 8 for short vectors, so that
+// small matrices neither idle most lanes of a warp nor occupy eight warps each).
+template <int T, int LPP>
+__global__ void __launch_bounds__(T)
 svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
                    int64_t batch, int rows, int cols, int* sweeps_out, int* fail_out, double* __restrict__ work,
                    unsigned long long* sweep_sum) {
@@ -701,12 +704,12 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   int* done_flag = zero_flag + n;
   const double* a_in = A + m * (int64_t)rows * cols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = kSvdGenThreads / 32;
+  constexpr int NW = T / 32;
 
   // G = A (tall: Gt[j][i] = A[i][j]) or A^T (wide: Gt[j][i] = A[j][i])
   __shared__ double red_max[NW];
   double amax = 0.0;
-  for (int64_t e = tid; e < (int64_t)rows * cols; e += kSvdGenThreads) amax = fmax(amax, fabs(a_in[e]));
+  for (int64_t e = tid; e < (int64_t)rows * cols; e += T) amax = fmax(amax, fabs(a_in[e]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(kFull, amax, o));
   if (lane == 0) red_max[warp] = amax;
@@ -714,12 +717,12 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   amax = 0.0;
   for (int w = 0; w < NW; w++) amax = fmax(amax, red_max[w]);
   const double pre = pow2_prescale(amax), post = 1.0 / pre;   // scale guard, exact power of two
-  for (int64_t e = tid; e < (int64_t)rows * cols; e += kSvdGenThreads) {
+  for (int64_t e = tid; e < (int64_t)rows * cols; e += T) {
     const double x = a_in[e] * pre;
     if (wide) Gt[e] = x;
     else { const int i = (int)(e / cols), j = (int)(e % cols); Gt[(size_t)j * mm + i] = x; }
   }
-  for (int64_t e = tid; e < (int64_t)n * n; e += kSvdGenThreads) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
+  for (int64_t e = tid; e < (int64_t)n * n; e += T) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
   __syncthreads();
 
   const double tol2 = ((double)mm * kEps) * ((double)mm * kEps);
@@ -730,30 +733,35 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
     int rotated = 0;
     sweeps++;
     for (int s = 0; s < n2 - 1; s++) {
-      for (int P = warp; P < n2 / 2; P += NW) {
+      for (int P = tid / LPP; P < n2 / 2; P += T / LPP) {
+        // the lanes of a group stay together; groups of one warp may diverge (different trip counts, bye pairs, rotate or not)
+        const unsigned gmask = LPP == 32 ? kFull : (((1u << LPP) - 1u) << ((lane / LPP) * LPP));
+        const int sub = tid % LPP;
         int p, q;
         rr_pair(n2, s, P, p, q);
         if (q >= n) continue;  // bye (odd n)
         double* gp = Gt + (size_t)p * mm;
         double* gq = Gt + (size_t)q * mm;
         double a = 0.0, b = 0.0, d = 0.0;
-        for (int i = lane; i < mm; i += 32) {
+        for (int i = sub; i < mm; i += LPP) {
           const double x = gp[i], y = gq[i];
           a = fma(x, x, a); b = fma(y, y, b); d = fma(x, y, d);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += shfl_xor(a, o); b += shfl_xor(b, o); d += shfl_xor(d, o); }
+        for (int o = LPP / 2; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(gmask, a, o); b += __shfl_xor_sync(gmask, b, o); d += __shfl_xor_sync(gmask, d, o);
+        }
         if (d * d > tol2 * a * b) {
           rotated = 1;
           const Rot r = make_rotation(a, b, d);
-          for (int i = lane; i < mm; i += 32) {
+          for (int i = sub; i < mm; i += LPP) {
             const double x = gp[i], y = gq[i];
             gp[i] = fma(r.c, x, -r.s * y);
             gq[i] = fma(r.s, x, r.c * y);
           }
           double* vp = Vt + (size_t)p * n;
           double* vq = Vt + (size_t)q * n;
-          for (int i = lane; i < n; i += 32) {
+          for (int i = sub; i < n; i += LPP) {
             const double x = vp[i], y = vq[i];
             vp[i] = fma(r.c, x, -r.s * y);
             vq[i] = fma(r.s, x, r.c * y);
@@ -779,7 +787,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
     if (lane == 0) sig[j] = sqrt(a);
   }
   __syncthreads();
-  for (int j = tid; j < n; j += kSvdGenThreads) {
+  for (int j = tid; j < n; j += T) {
     const double sj = sig[j];
     int rank = 0;
     double smax = 0.0;
@@ -815,15 +823,15 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   const int uld = wide ? n : mm;
   const double* vsrc = wide ? Gt : Vt;
   const int vld = wide ? mm : n;
-  for (int64_t e = tid; e < (int64_t)rows * n; e += kSvdGenThreads) {
+  for (int64_t e = tid; e < (int64_t)rows * n; e += T) {
     const int i = (int)(e / n), l = (int)(e % n);
     u_out[e] = usrc[(size_t)perm[l] * uld + i];
   }
-  for (int64_t e = tid; e < (int64_t)n * cols; e += kSvdGenThreads) {
+  for (int64_t e = tid; e < (int64_t)n * cols; e += T) {
     const int l = (int)(e / cols), j = (int)(e % cols);
     v_out[e] = vsrc[(size_t)perm[l] * vld + j];
   }
-  for (int l = tid; l < n; l += kSvdGenThreads) SV[m * n + l] = zero_flag[perm[l]] ? 0.0 : sig[perm[l]] * post;
+  for (int l = tid; l < n; l += T) SV[m * n + l] = zero_flag[perm[l]] ? 0.0 : sig[perm[l]] * post;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1060,18 +1068,24 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
   }
   const size_t per_matrix = sizeof(double) * svd_gen_scratch_doubles(rows, cols);
   if (per_matrix <= kSvdGenSmemLimit) {  // same kernel, scratch in shared memory (L1 instead of L2 latency on every access)
-    static bool attr_done[64] = {false};
-    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(svd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvdGenSmemLimit);
+    const int mmax = rows > cols ? rows : cols, nmin = rows < cols ? rows : cols;
+    const int pairs = (nmin + 1) / 2;
+    // short vectors: 8 or 16 lanes per column pair and only as many warps as the pairs of a step need
+    auto go = [&](auto kernel, int threads) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvdGenSmemLimit);
       if (e != cudaSuccess) return e;
-      attr_done[dev] = true;
-    }
-    svd_generic_kernel<<<(unsigned)batch, kSvdGenThreads, per_matrix, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, nullptr, ssum);
-    return cudaGetLastError();
+      kernel<<<(unsigned)batch, threads, per_matrix, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, nullptr, ssum);
+      return cudaGetLastError();
+    };
+    if (mmax <= 16 && pairs <= 8) return go(svd_generic_kernel<64, 8>, 64);
+    if (mmax <= 16) return go(svd_generic_kernel<128, 8>, 128);
+    if (mmax <= 32 && pairs <= 8) return go(svd_generic_kernel<128, 16>, 128);
+    if (mmax <= 32) return go(svd_generic_kernel<256, 16>, 256);
+    return go(svd_generic_kernel<256, 32>, 256);
   }
   const size_t need = per_matrix * (size_t)batch;
   if (work == nullptr || work_bytes < need) return cudaErrorInvalidValue;
-  svd_generic_kernel<<<(unsigned)batch, kSvdGenThreads, 0, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, work, ssum);
+  svd_generic_kernel<256, 32><<<(unsigned)batch, 256, 0, s>>>(A, U, sv, V, batch, rows, cols, sweeps, fail, work, ssum);
   return cudaGetLastError();
 }
 
