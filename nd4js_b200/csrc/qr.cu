@@ -563,7 +563,7 @@ cudaError_t launch_qr_inplace(cudaStream_t s, const double* A, const double* Y, 
     const char* ev = getenv("ND4B_QR_PADDED");
     padded = ev ? atoi(ev) : 1;
   }
-  if (padded && M <= 64 && N <= 32 && L >= 1 && L <= 8 && M * N >= 128)
+  if (padded && M <= 64 && N <= 32 && L >= 1 && L <= 8)
     return launch_qr_inplace_blocked(s, A, Y, R, QtY, batch, M, N, L);
   if (qr_smem_bytes(M, N, L, false) <= kQrSmemLimit) return launch_qr_smem<false>(s, A, Y, nullptr, R, QtY, batch, M, N, L);
   qr_inplace_kernel<<<(unsigned)batch, kQrGenThreads, 0, s>>>(A, Y, R, QtY, batch, M, N, L);
@@ -727,9 +727,9 @@ cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int
     const char* ev = getenv("ND4B_QR_PADDED");
     padded = ev ? atoi(ev) : 1;
   }
-  if (padded && rows <= 64 && cols <= 32 && rows * cols >= 128 && batch <= 0x7fffffffLL)
-    return launch_qr_padded_blocked(s, A, Q, R, batch, rows, cols);
   if (padded && rows <= 8 && cols <= 8 && batch >= 64) return launch_qr_tiny(s, A, Q, R, batch, rows, cols);
+  if (padded && rows <= 64 && cols <= 32 && batch <= 0x7fffffffLL)
+    return launch_qr_padded_blocked(s, A, Q, R, batch, rows, cols);
   if (batch <= 0x7fffffffLL && qr_smem_bytes(rows, cols, 0, true) <= kQrSmemLimit)
     return launch_qr_smem<true>(s, A, nullptr, Q, R, nullptr, batch, rows, cols, 0);
   const int L = rows < cols ? rows : cols;
