@@ -14,7 +14,7 @@ hot path over one batch.  Weak scaling: every rank (one process per GPU) owns it
   roofline  dominant kernel matmul32_kernel: 24 576 algorithmic bytes per matrix / launch time vs measured HBM peak
   cpu_baseline  the oracle (C restatement of the reference's JS loops) on one host core (the reference is
             single-threaded), on a bounded sample, rank 0 / N=1 only
-`--workload c1|c3|c4|c5` times the other BASELINE configs the same way; `others` in the default line
+`--workload c1|c3|c4|c5` times the other BASELINE configs the same way (s3, l4, i4: the 'next' rows; g4k: compute-bound probe); `others` in the default line
 carries their kernel-only numbers.
 """
 import argparse
@@ -40,6 +40,9 @@ WORKLOADS = {
     "s3": ("batched nd.la.cholesky_solve float64 L[262144,16,16], y[262144,16,1]", 262144, 2048 + 128 + 128, 2 * 16 * 16),
     # next row 8f-1: least squares from C4's factors; bytes: Q, R, y in, x out
     "l4": ("batched nd.la.qr_lstsq float64 Q[65536,64,32], R[65536,32,32], y[65536,64,1]", 65536, (2048 + 1024 + 64 + 32) * 8, 2 * 64 * 32 + 32 * 32),
+    # next row 8f-3: R and Q^T y without forming Q; bytes: A, y in; R (M x N), Q^T y out; flop: Householder R phase + reflectors on y
+    "i4": ("batched nd.la._qr_decomp_inplace float64 A[65536,64,32], y[65536,64,1]", 65536, (2048 + 64 + 2048 + 64) * 8,
+           2 * 64 * 32 * 32 - 2 * 32 ** 3 / 3.0 + 4 * 64 * 32),
     # compute-bound probe of the same matmul kernel family (north_star: matmul vs FP64 tensor-core peak)
     "g4k": ("nd.la.matmul float64 4096x4096 . 4096x4096 single matrix (compute-bound probe)", 1, 3 * 4096 * 4096 * 8, 2 * 4096 ** 3),
 }
@@ -126,7 +129,7 @@ def run_reference(args):
     nd4ref.build()
     desc, units, bpu, fpu = WORKLOADS[args.workload]
     rng = np.random.default_rng(3)
-    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24, "g4k": 1, "s3": 65536, "l4": 8192}[args.workload]
+    sample = {"c1": 1, "c2": 8192, "c3": 32768, "c4": 2048, "c5": 24, "g4k": 1, "s3": 65536, "l4": 8192, "i4": 2048}[args.workload]
     fn, data = _ref_case(args.workload, sample, rng, nd4ref)
     for _ in range(min(args.warmup, 1)):
         fn(*data)
@@ -165,6 +168,8 @@ def _ref_case(name, n, rng, nd4ref):
     if name == "l4":
         q, r = np.linalg.qr(rng.uniform(-1, 1, (n, 64, 32)))
         return nd4ref.qr_lstsq, (q, r, rng.uniform(-1, 1, (n, 64, 1)))
+    if name == "i4":
+        return nd4ref.qr_decomp_inplace, (rng.uniform(-1, 1, (n, 64, 32)), rng.uniform(-1, 1, (n, 64, 1)))
     if name == "s3":
         g = rng.uniform(-1, 1, (n, 16, 16))
         return nd4ref.cholesky_solve, (np.linalg.cholesky(g @ g.transpose(0, 2, 1) + 16 * np.eye(16)), rng.uniform(-1, 1, (n, 16, 1)))
@@ -205,6 +210,9 @@ class DeviceCase:
             self.a, self.r = self.a.contiguous(), self.r.contiguous()
             self.b = u(units, 64, 1)
             self.out = [torch.empty(units, 32, 1, **f64)]
+        elif name == "i4":
+            self.a, self.b = u(units, 64, 32), u(units, 64, 1)
+            self.out = [torch.empty(units, 64, 32, **f64), torch.empty(units, 64, 1, **f64)]
         elif name == "c4":
             self.a = u(units, 64, 32)
             self.out = [torch.empty(units, 64, 32, **f64), torch.empty(units, 32, 32, **f64)]
@@ -242,6 +250,8 @@ class DeviceCase:
             rc = L.nd4b_dev_tri_solve_f64(d, s, 2, p(self.a), 256, p(self.b), 16, p(self.out[0]), self.units, 16, 1)
         elif self.name == "l4":
             rc = L.nd4b_dev_qr_lstsq_f64(d, s, p(self.a), p(self.r), p(self.b), p(self.out[0]), self.units, 64, 32, 32, 1)
+        elif self.name == "i4":
+            rc = L.nd4b_dev_qr_inplace_f64(d, s, p(self.a), p(self.b), p(self.out[0]), p(self.out[1]), self.units, 64, 32, 1)
         elif self.name == "c4":
             rc = L.nd4b_dev_qr_f64(d, s, p(self.a), p(self.out[0]), p(self.out[1]), self.units, 64, 32, None, 0)
         else:
@@ -306,6 +316,11 @@ def host_case(name, nd, units):
         lp, yp = C.c_void_p(ls.ctypes.data), C.c_void_p(ys.ctypes.data)
         return ((lambda: L.nd4b_tri_solve_f64(2, p(l), lp, 3, p(y), yp, 3, p(x), yp, 3)), (l.numel() + y.numel()) * 8, x.numel() * 8,
                 (l, y, x, ls, ys))
+    if name == "i4":
+        a, y = pinned((units, 64, 32), rng.uniform(-1, 1, (units, 64, 32))), pinned((units, 64, 1), rng.uniform(-1, 1, (units, 64, 1)))
+        r, qty = pinned((units, 64, 32)), pinned((units, 64, 1))
+        return ((lambda: L.nd4b_qr_inplace_f64(p(a), p(y), p(r), p(qty), units, 64, 32, 1)), (a.numel() + y.numel()) * 8,
+                (r.numel() + qty.numel()) * 8, (a, y, r, qty))
     if name == "c4":
         a, q, r = pinned((units, 64, 32), rng.uniform(-1, 1, (units, 64, 32))), pinned((units, 64, 32)), pinned((units, 32, 32))
         return (lambda: L.nd4b_qr_f64(p(a), p(q), p(r), units, 64, 32)), a.numel() * 8, (q.numel() + r.numel()) * 8, (a, q, r)
@@ -429,7 +444,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         kernel = {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c3": "chol16_kernel",
-                  "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel", "s3": "trisolve16_kernel", "l4": "qr_lstsq32_kernel"}[args.workload]
+                  "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel", "s3": "trisolve16_kernel", "l4": "qr_lstsq32_kernel", "i4": "qr64x32_inplace_kernel"}[args.workload]
         traffic, traffic_src = NCU_TRAFFIC_BYTES.get(args.workload, (None, None))
         if args.workload in ("c1", "g4k", "c5"):
             # compute-bound configs: against the FP64 pipe — DMMA for the GEMMs, DFMA for the Jacobi SVD; both
@@ -453,7 +468,7 @@ def run_ours(args):
             "gflops": value * flop_unit / 1e9,
             "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timing": "host wall clock around the blocking C-ABI call, barrier+sync both sides, max over ranks",
-                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1", "s3": "tri_solve", "l4": "qr_lstsq"}[args.workload],
+                    "api": "nd4b_%s_f64 (host buffers, pinned)" % {"c1": "matmul", "c2": "matmul", "g4k": "matmul", "c3": "cholesky", "c4": "qr", "c5": "svd_jac1", "s3": "tri_solve", "l4": "qr_lstsq", "i4": "qr_inplace"}[args.workload],
                     "rank_cpus_near_gpu": numa},
             "gpu_launches": args.steps + int(e2e_launches),
             "roofline": roofline,
@@ -474,7 +489,7 @@ def run_ours(args):
     # ---------------- the other BASELINE configs, kernel-only, short ----------------
     if args.workload == "c2" and not args.no_others:
         others = {}
-        for name in ("c1", "g4k", "c3", "s3", "c4", "l4", "c5"):
+        for name in ("c1", "g4k", "c3", "s3", "c4", "l4", "i4", "c5"):
             d2, u2, b2, f2 = WORKLOADS[name]
             c2 = DeviceCase(name, torch, lib, local, u2)
             barrier()
@@ -500,7 +515,7 @@ def run_ours(args):
         import numpy as np
         from oracle import nd4ref
         nd4ref.build()
-        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96, "g4k": 1, "s3": 262144, "l4": 16384}[args.workload]
+        sample = {"c1": 1, "c2": 65536, "c3": 262144, "c4": 8192, "c5": 96, "g4k": 1, "s3": 262144, "l4": 16384, "i4": 8192}[args.workload]
         fn, data = _ref_case(args.workload, sample, np.random.default_rng(3), nd4ref)
         reps, t0 = 0, time.perf_counter()
         while True:
