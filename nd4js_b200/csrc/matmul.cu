@@ -520,6 +520,7 @@ static cudaError_t launch_matmul_small(cudaStream_t s, const double* A, const do
   if (I == 4 && K == 4 && J == 4) return launch_matmul_small_t<4, 4, 4>(s, A, B, C, batch, I, K, J, map);
   if (I == 3 && K == 3 && J == 3) return launch_matmul_small_t<3, 3, 3>(s, A, B, C, batch, I, K, J, map);
   if (I == 2 && K == 2 && J == 2) return launch_matmul_small_t<2, 2, 2>(s, A, B, C, batch, I, K, J, map);
+  if (I == 5 && K == 5 && J == 5) return launch_matmul_small_t<5, 5, 5>(s, A, B, C, batch, I, K, J, map);
   if (I == 4 && K == 4 && J == 1) return launch_matmul_small_t<4, 4, 1>(s, A, B, C, batch, I, K, J, map);
   if (I == 3 && K == 3 && J == 1) return launch_matmul_small_t<3, 3, 1>(s, A, B, C, batch, I, K, J, map);
   return launch_matmul_small_t<0, 0, 0>(s, A, B, C, batch, I, K, J, map);
