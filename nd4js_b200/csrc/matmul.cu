@@ -582,6 +582,71 @@ static cudaError_t launch_matmul_frag8(cudaStream_t s, const double* A, const do
   return cudaGetLastError();
 }
 
+// The same idea for odd or unaligned operands up to 8*TI x 8*TK x 8*TJ (9x9, 17x17, ...), which the tiled kernels can
+// only serve through their scalar path on tiles of 16 or 32: TI x TJ accumulator tiles per warp, every fragment an
+// 8-byte load predicated on the matrix bounds (zeros outside), two matrices per warp in flight.
+template <int TI, int TK, int TJ>
+__global__ void __launch_bounds__(kFragWarps * 32)
+matmul_frag_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                   int64_t batch, int I, int K, int J, BatchMap map) {
+  constexpr int U = 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t m0 = ((int64_t)blockIdx.x * kFragWarps + warp) * U;
+  if (m0 >= batch) return;  // warp-uniform
+  double af[U][TI][2 * TK], bf[U][2 * TK][TJ];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int64_t m = m0 + u;
+    int64_t ao = 0, bo = 0;
+    const bool live = m < batch;
+    if (live) decode_batch(map, m, ao, bo);
+    const double* a = A + ao;
+    const double* b = B + bo;
+#pragma unroll
+    for (int i = 0; i < TI; i++)
+#pragma unroll
+      for (int k = 0; k < 2 * TK; k++) {
+        const int row = 8 * i + g, kk = 4 * k + t;
+        af[u][i][k] = (live && row < I && kk < K) ? ldg1_stream(a + row * K + kk) : 0.0;
+      }
+#pragma unroll
+    for (int k = 0; k < 2 * TK; k++)
+#pragma unroll
+      for (int j = 0; j < TJ; j++) {
+        const int kk = 4 * k + t, col = 8 * j + g;
+        bf[u][k][j] = (live && kk < K && col < J) ? ldg1_stream(b + kk * J + col) : 0.0;
+      }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int64_t m = m0 + u;
+    if (m >= batch) break;   // warp-uniform
+    double* c = C + m * (int64_t)(I * J);
+#pragma unroll
+    for (int i = 0; i < TI; i++)
+#pragma unroll
+      for (int j = 0; j < TJ; j++) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * TK; k++) dmma884(c0, c1, af[u][i][k], bf[u][k][j]);
+        const int row = 8 * i + g, col = 8 * j + 2 * t;
+        if (row < I && col < J) c[row * J + col] = c0;
+        if (row < I && col + 1 < J) c[row * J + col + 1] = c1;
+      }
+  }
+}
+
+template <int TI, int TK, int TJ>
+static cudaError_t launch_matmul_frag(cudaStream_t s, const double* A, const double* B, double* C,
+                                      int64_t batch, int I, int K, int J, const BatchMap& map) {
+  const int per_cta = kFragWarps * 2;
+  const int64_t grid = (batch + per_cta - 1) / per_cta;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  matmul_frag_kernel<TI, TK, TJ><<<(unsigned)grid, kFragWarps * 32, 0, s>>>(A, B, C, batch, I, K, J, map);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, double* C,
                           int64_t batch, int I, int K, int J, const BatchMap& map, int sm_count) {
   if (batch <= 0) return cudaSuccess;
@@ -600,6 +665,10 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
     return launch_matmul_frag8(s, A, B, C, batch, I, K, J, map);
   }
   const bool vec = aligned && str_even && (K % 2 == 0) && (J % 2 == 0) && (((int64_t)I * J) % 2 == 0);
+  if (!vec && batch >= 256) {   // odd / unaligned small operands: fragments straight from HBM instead of the scalar tile path
+    if (I <= 16 && K <= 16 && J <= 16) return launch_matmul_frag<2, 2, 2>(s, A, B, C, batch, I, K, J, map);
+    if (I <= 24 && K <= 24 && J <= 24) return launch_matmul_frag<3, 3, 3>(s, A, B, C, batch, I, K, J, map);
+  }
   // Tile choice: 64x64 tiles when they still give >= 2 CTAs per SM, else 64x32 (4 warps of 16x32) to
   // spread a single mid-sized product (e.g. 512^3 -> 128 CTAs) over the 148 SMs, else 16x16 per warp.
   if (vec && K >= 64) {
