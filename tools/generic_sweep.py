@@ -52,7 +52,7 @@ for (b, n) in [(65536, 32), (16384, 64), (262144, 8)]:
     ms = timeit(lambda: lib.nd4b_dev_cholesky_f64(0, st, p(s), p(out), b, n, None))
     print("chol    [%6d,%3d,%3d]: %8.3f ms  %9.0f matrices/s  %6.1f GB/s" % (b, n, n, ms, b / ms * 1e3, 2 * n * n * 8 * b / ms / 1e6))
 for (b, i, k, j) in [(1048576, 8, 8, 8), (262144, 16, 16, 16), (262144, 16, 32, 8), (65536, 32, 32, 32), (65536, 24, 40, 24), (16384, 64, 64, 64), (4096, 128, 128, 128),
-                     (1048576, 4, 4, 4), (1048576, 3, 3, 3), (1048576, 4, 4, 1), (1048576, 3, 3, 1), (1048576, 5, 5, 5)]:
+                     (1048576, 4, 4, 4), (1048576, 3, 3, 3), (1048576, 4, 4, 1), (1048576, 3, 3, 1), (1048576, 5, 5, 5), (552336, 9, 9, 9), (154807, 17, 17, 17), (84573, 23, 23, 23)]:
     a, bb = torch.rand(b, i, k, **f64), torch.rand(b, k, j, **f64)
     c = torch.empty(b, i, j, **f64)
     ms = timeit(lambda: lib.nd4b_dev_matmul_f64(0, st, p(a), i * k, p(bb), k * j, p(c), b, i, k, j))
