@@ -56,6 +56,9 @@ const char* nd4b_version(void);
  * can keep Float64Array storage DMA-able and skip the staging copy. */
 void* nd4b_host_alloc(size_t bytes);
 void nd4b_host_free(void* p);
+/* Freed blocks are cached for reuse (page-locking costs more than the copy it saves; at most ND4B_PINNED_CACHE_MB,
+ * default 8192, of idle blocks); this releases the idle ones. */
+void nd4b_host_trim(void);
 
 /* Bytes of pipeline chunk per device stream (default 32 MiB); also ND4B_CHUNK_MB in the environment. */
 int nd4b_set_chunk_bytes(size_t bytes);
@@ -131,6 +134,27 @@ int nd4b_qr_lstsq_f64(const double* Q, const double* R, const double* Y, double*
 int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
                       int64_t batch, int rows, int cols, int* sweeps_out);
 
+/* ---- nd.la.svd_rank / svd_lstsq / svd_solve — src/la/svd.js:31-58, 103-226, 61-100 ------------------------------- */
+
+/* rank[batch] (int32): number of leading singular values with |sv_r| > sqrt(eps) * |sv_0| (the scan stops at the first one
+ * at or below the cut, svd.js:44-52).  ND4B_E_NAN_INPUT ('svd_rank(): NaN or Infinity encountered.') when a non-finite entry
+ * is met before the cut, as the reference throws. */
+int nd4b_svd_rank_f64(const double* sv, int32_t* rank, int64_t batch, int n);
+
+/* Validation (the reference's checks and texts, svd.js:112-147) and broadcast result shape [..., I, J] of svd_lstsq for
+ * U[...,N,M], sv[...,M], V[...,M,I], y[...,N,J]; x_shape must hold max(u_ndim, sv_ndim + 1, v_ndim, y_ndim) entries. */
+int nd4b_svd_lstsq_shape(const int32_t* u_shape, int u_ndim, const int32_t* sv_shape, int sv_ndim,
+                         const int32_t* v_shape, int v_ndim, const int32_t* y_shape, int y_ndim,
+                         int32_t* x_shape, int* x_ndim);
+
+/* X = V^T diag(1/sv[:R]) U^T Y with R the rank cut above, all four operands broadcast independently over the leading dims.
+ * One fused kernel; bit-identical with the reference (the sums of svd.js:177-193 in their order, products and sums rounded
+ * separately, IEEE division).  svd_solve is this call plus the squareness check, which stays in the shim (svd.js:74-75; the
+ * reference's singularity scan :87-95 never runs because its loop variable starts undefined). */
+int nd4b_svd_lstsq_f64(const double* U, const int32_t* u_shape, int u_ndim, const double* sv, const int32_t* sv_shape, int sv_ndim,
+                       const double* V, const int32_t* v_shape, int v_ndim, const double* Y, const int32_t* y_shape, int y_ndim,
+                       double* X, const int32_t* x_shape, int x_ndim);
+
 /* ---- nd.la.tril_solve / triu_solve (src/la/tri.js:156-293) and nd.la.cholesky_solve (src/la/cholesky.js:75-144) ---- */
 
 #define ND4B_TRIL_SOLVE     0   /* X = L^-1 Y, forward substitution  (_tril_solve, tri.js:45-71)          */
@@ -162,6 +186,9 @@ int nd4b_dev_qr_lstsq_f64(int device, void* stream, const double* Q, const doubl
                           int64_t batch, int N, int M, int I, int J);
 int nd4b_dev_qr_inplace_f64(int device, void* stream, const double* A, const double* Y, double* R, double* QtY,
                             int64_t batch, int M, int N, int L);
+/* All operands with the same batch; fail_flag (device int32, may be NULL) is set when a non-finite sv precedes the cut. */
+int nd4b_dev_svd_lstsq_f64(int device, void* stream, const double* U, const double* sv, const double* V, const double* Y, double* X,
+                           int64_t batch, int N, int M, int I, int J, int* fail_flag);
 /* sweeps (device int32, may be NULL): atomicMax of sweeps used.  workspace as reported below. */
 int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, double* sv, double* V,
                           int64_t batch, int rows, int cols, int* sweeps,

@@ -7,7 +7,8 @@ The arithmetic lives in libnd4b.so (hand-written CUDA, C ABI in include/nd4b.h);
 host-side mirror of the reference's operator interface plus the batch partitioner.
 """
 from . import la  # noqa: F401
-from ._lib import Nd4bError, init, load, stats  # noqa: F401
+from ._lib import Nd4bError, host_trim, init, load, pinned_array, pinned_empty, stats  # noqa: F401
 from .nd_array import NDArray, asarray, from_numpy  # noqa: F401
 
-__all__ = ["la", "NDArray", "asarray", "from_numpy", "init", "load", "stats", "Nd4bError"]
+__all__ = ["la", "NDArray", "asarray", "from_numpy", "init", "load", "stats", "Nd4bError", "pinned_array", "pinned_empty",
+           "host_trim"]

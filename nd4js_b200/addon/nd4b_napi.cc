@@ -170,6 +170,49 @@ napi_value SvdJac1(napi_env env, napi_callback_info info) {
   napi_value r; napi_create_int32(env, sweeps, &r); return r;
 }
 
+// svdRank(sv:Float64Array, rank:Int32Array, n) — nd4b_svd_rank_f64 (svd.js:31-58)
+napi_value SvdRank(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value v[3];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 sv; I32 rank; int64_t n;
+  if (argc < 3 || !get_f64(env, v[0], &sv) || !get_i32(env, v[1], &rank) || !get_int(env, v[2], &n)) return nullptr;
+  if (n < 1 || (int64_t)sv.n != (int64_t)rank.n * n) { napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr; }
+  if (nd4b_svd_rank_f64(sv.p, rank.p, (int64_t)rank.n, (int)n)) return fail(env);
+  return undefined(env);
+}
+
+// svdLstsqShape(uShape, svShape, vShape, yShape, xShape) -> ndim: the reference's checks and texts (svd.js:112-147)
+napi_value SvdLstsqShape(napi_env env, napi_callback_info info) {
+  size_t argc = 5; napi_value v[5];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  I32 us, ss, vs, ys, xs;
+  if (argc < 5 || !get_i32(env, v[0], &us) || !get_i32(env, v[1], &ss) || !get_i32(env, v[2], &vs) || !get_i32(env, v[3], &ys) ||
+      !get_i32(env, v[4], &xs)) return nullptr;
+  size_t need = us.n > ss.n + 1 ? us.n : ss.n + 1;
+  if (vs.n > need) need = vs.n;
+  if (ys.n > need) need = ys.n;
+  if (xs.n < need) { napi_throw_error(env, nullptr, "nd4b: xShape too short"); return nullptr; }
+  int nd = 0;
+  if (nd4b_svd_lstsq_shape(us.p, (int)us.n, ss.p, (int)ss.n, vs.p, (int)vs.n, ys.p, (int)ys.n, xs.p, &nd)) return fail(env);
+  napi_value r; napi_create_int32(env, nd, &r); return r;
+}
+
+// svdLstsq(U, uShape, sv, svShape, V, vShape, Y, yShape, X, xShape) — nd4b_svd_lstsq_f64 (svd.js:103-226)
+napi_value SvdLstsq(napi_env env, napi_callback_info info) {
+  size_t argc = 10; napi_value v[10];
+  napi_get_cb_info(env, info, &argc, v, nullptr, nullptr);
+  F64 u, s, vt, y, x; I32 us, ss, vs, ys, xs;
+  if (argc < 10 || !get_f64(env, v[0], &u) || !get_i32(env, v[1], &us) || !get_f64(env, v[2], &s) || !get_i32(env, v[3], &ss) ||
+      !get_f64(env, v[4], &vt) || !get_i32(env, v[5], &vs) || !get_f64(env, v[6], &y) || !get_i32(env, v[7], &ys) ||
+      !get_f64(env, v[8], &x) || !get_i32(env, v[9], &xs)) return nullptr;
+  if ((int64_t)u.n != prod(us) || (int64_t)s.n != prod(ss) || (int64_t)vt.n != prod(vs) || (int64_t)y.n != prod(ys) || (int64_t)x.n != prod(xs)) {
+    napi_throw_error(env, nullptr, "nd4b: data length does not match shape"); return nullptr;
+  }
+  if (nd4b_svd_lstsq_f64(u.p, us.p, (int)us.n, s.p, ss.p, (int)ss.n, vt.p, vs.p, (int)vs.n, y.p, ys.p, (int)ys.n, x.p, xs.p, (int)xs.n))
+    return fail(env);
+  return undefined(env);
+}
+
 // triSolve(op, T, tShape, Y, yShape, X, xShape)   op 0 tril_solve, 1 triu_solve, 2 cholesky_solve
 napi_value TriSolve(napi_env env, napi_callback_info info) {
   size_t argc = 7; napi_value v[7];
@@ -237,6 +280,9 @@ napi_value RegisterAll(napi_env env, napi_value exports) {
       {"qrInplace", nullptr, QrInplace, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"triSolve", nullptr, TriSolve, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"svdJac1", nullptr, SvdJac1, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"svdRank", nullptr, SvdRank, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"svdLstsqShape", nullptr, SvdLstsqShape, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"svdLstsq", nullptr, SvdLstsq, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"pinnedFloat64Array", nullptr, PinnedFloat64Array, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"init", nullptr, Init, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"deviceCount", nullptr, DeviceCount, nullptr, nullptr, nullptr, napi_default, nullptr},

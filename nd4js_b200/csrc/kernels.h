@@ -19,6 +19,15 @@ struct BatchMap {
   int64_t b_str[8];
 };
 
+// The same odometer for the four independently broadcast operands of svd_lstsq (U, sv, V, y; src/la/svd.js:201-218).
+struct BatchMap4 {
+  int nd;
+  int64_t base;
+  int64_t lin[4];     // >= 0: offset = local_index * lin; < 0: resident operand addressed through the odometer
+  int64_t size[8];
+  int64_t str[4][8];
+};
+
 cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, double* C,
                           int64_t batch, int I, int K, int J, const BatchMap& map, int sm_count);
 
@@ -33,6 +42,12 @@ cudaError_t launch_tri_solve(cudaStream_t s, int op, const double* T, const doub
 // qr_lstsq for thin factors (M, I <= 32), same batch for Q[N,M], R[M,I], Y[N,J]; X[I,J]; bit-exact with the reference
 cudaError_t launch_qr_lstsq(cudaStream_t s, const double* Q, const double* R, const double* Y, double* X,
                             int64_t batch, int N, int M, int I, int J);
+
+// svd_lstsq (src/la/svd.js:103-226): X[batch,I,J] from U[N,M], sv[M], V[M,I], Y[N,J] addressed through `map`; *fail is set
+// when a non-finite singular value is met before the rank cut.  svd_rank (src/la/svd.js:31-58): rank[batch] (int32).
+cudaError_t launch_svd_lstsq(cudaStream_t s, const double* U, const double* SV, const double* V, const double* Y, double* X,
+                             int64_t batch, int N, int M, int I, int J, const BatchMap4& map, int* fail);
+cudaError_t launch_svd_rank(cudaStream_t s, const double* SV, int* rank, int64_t batch, int M, int* fail);
 
 size_t qr_workspace_bytes(int64_t batch, int rows, int cols);
 cudaError_t launch_qr(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols,

@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <unordered_map>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -22,6 +24,7 @@
 namespace {
 
 using nd4b::BatchMap;
+using nd4b::BatchMap4;
 
 thread_local std::string g_err;
 
@@ -57,7 +60,7 @@ const char* ref_message(int code) {
   } while (0)
 
 constexpr int kSlots = 3;     // pipeline depth per device: chunk c runs on slot c % kSlots
-constexpr int kMaxIn = 3, kMaxOut = 3;
+constexpr int kMaxIn = 4, kMaxOut = 3;
 constexpr int kOutBase = kMaxIn, kWorkBuf = kMaxIn + kMaxOut;
 constexpr int kMaxBuf = kWorkBuf + 1;  // device buffers per slot: up to 3 inputs, 3 outputs, 1 workspace
 
@@ -135,8 +138,8 @@ struct Device {
   int id = -1;
   int sm_count = 0;
   Slot slots[kSlots];
-  void* resident[2] = {nullptr, nullptr};  // whole broadcast operands of matmul
-  size_t resident_cap[2] = {0, 0};
+  void* resident[4] = {nullptr, nullptr, nullptr, nullptr};  // whole broadcast operands (matmul, solves: 2; svd_lstsq: 4)
+  size_t resident_cap[4] = {0, 0, 0, 0};
   long long* d_info = nullptr;              // cholesky failure key
   int* d_ints = nullptr;                    // [0] = svd sweeps, [1] = svd fail flag
 };
@@ -160,6 +163,29 @@ struct Timer {
 
 Context* g_ctx = nullptr;
 std::mutex g_init_mu;
+
+// cache of idle page-locked blocks behind nd4b_host_alloc / nd4b_host_free
+struct PinnedCache {
+  std::mutex mu;
+  std::map<size_t, std::vector<void*>> idle;   // size class -> blocks
+  std::unordered_map<void*, size_t> live;      // blocks handed out -> size class
+  size_t idle_bytes = 0;
+  size_t limit() const {
+    static const size_t v = [] {
+      const char* e = getenv("ND4B_PINNED_CACHE_MB");
+      return (size_t)(e ? std::max(0L, atol(e)) : 8192L) << 20;
+    }();
+    return v;
+  }
+} g_pin;
+
+size_t pinned_class(size_t bytes) {
+  if (bytes < 4096) return 4096;
+  if (bytes >= (1u << 20)) return (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+  size_t c = 4096;
+  while (c < bytes) c <<= 1;
+  return c;
+}
 
 int ensure(Slot& s, int i, size_t bytes) {
   if (s.cap[i] >= bytes) return 0;
@@ -304,8 +330,31 @@ static int64_t next_chunk_units(int64_t full, int chunk_index, int64_t remaining
   return std::min(cnt, remaining);
 }
 
+// After a failure nothing that was queued may still be running when the call returns: the caller is free to release or
+// reuse its buffers, and async copies into them (or kernels on other slots / devices) would write into freed memory.
+void quiesce(Context* ctx) {
+  for (auto& dv : ctx->devs) {
+    cudaSetDevice(dv.id);
+    for (auto& sl : dv.slots) {
+      cudaStreamSynchronize(sl.stream);
+      sl.n_pending = 0;
+    }
+  }
+  cudaGetLastError();
+}
+
+int run_pipeline_body(Context* ctx, int64_t units, const std::vector<Stream1>& ins, const std::vector<Stream1>& outs,
+                      size_t work_bytes_per_unit, const std::function<int(const ChunkArgs&)>& launch);
+
 int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, const std::vector<Stream1>& outs,
                  size_t work_bytes_per_unit, const std::function<int(const ChunkArgs&)>& launch) {
+  const int rc = run_pipeline_body(ctx, units, ins, outs, work_bytes_per_unit, launch);
+  if (rc) { const std::string keep = g_err; quiesce(ctx); g_err = keep; }
+  return rc;
+}
+
+int run_pipeline_body(Context* ctx, int64_t units, const std::vector<Stream1>& ins, const std::vector<Stream1>& outs,
+                      size_t work_bytes_per_unit, const std::function<int(const ChunkArgs&)>& launch) {
   const int nd = (int)ctx->devs.size();
   size_t in_bytes_unit = 0, out_bytes_unit = 0;
   for (auto& s : ins) in_bytes_unit += (size_t)s.elems * 8;
@@ -408,6 +457,16 @@ int run_pipeline(Context* ctx, int64_t units, const std::vector<Stream1>& ins, c
   return ND4B_OK;
 }
 
+// Resets a per-device accumulator (cholesky failure key, svd sweep / failure words) on a slot stream and waits for it: the
+// slot streams are non-blocking, so a reset on the legacy stream would have no ordering with the kernels that later
+// atomicMin / atomicMax into the word.
+int reset_device_words(Device& d, void* dst, const void* src, size_t bytes) {
+  CU(cudaSetDevice(d.id));
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.slots[0].stream));
+  CU(cudaStreamSynchronize(d.slots[0].stream));
+  return ND4B_OK;
+}
+
 int check_cuda_launch(cudaError_t e, Context* ctx, int n = 1) {
   if (e != cudaSuccess) return fail(ND4B_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   if (ctx) ctx->launches += n;
@@ -496,15 +555,66 @@ int nd4b_device_count(void) {
   return g_ctx ? (int)g_ctx->devs.size() : 0;
 }
 
+// Page-locking is expensive (cudaHostAlloc of 512 MiB takes longer than copying it), and every nd.la.* call returns fresh
+// arrays: freed blocks are therefore kept in a small cache and handed out again (exact size class: the next multiple of
+// 1 MiB for large blocks, the next power of two below that), so that a caller that drops one result and asks for the next
+// gets the same pages back.  Bounded by ND4B_PINNED_CACHE_MB (default 8192) of idle blocks; nd4b_host_trim() empties it.
 void* nd4b_host_alloc(size_t bytes) {
-  void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
-    g_err = std::string("nd4b_host_alloc: ") + cudaGetErrorString(cudaGetLastError());
-    return nullptr;
+  const size_t cls = pinned_class(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_pin.mu);
+    auto it = g_pin.idle.find(cls);
+    if (it != g_pin.idle.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      g_pin.idle_bytes -= cls;
+      g_pin.live[p] = cls;
+      return p;
+    }
   }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    nd4b_host_trim();   // give the idle blocks back and retry once
+    if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) {
+      g_err = std::string("nd4b_host_alloc: ") + cudaGetErrorString(cudaGetLastError());
+      return nullptr;
+    }
+  }
+  std::lock_guard<std::mutex> lk(g_pin.mu);
+  g_pin.live[p] = cls;
   return p;
 }
-void nd4b_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void nd4b_host_free(void* p) {
+  if (!p) return;
+  size_t cls = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_pin.mu);
+    auto it = g_pin.live.find(p);
+    if (it != g_pin.live.end()) {
+      cls = it->second;
+      g_pin.live.erase(it);
+      if (g_pin.idle_bytes + cls <= g_pin.limit()) {
+        g_pin.idle[cls].push_back(p);
+        g_pin.idle_bytes += cls;
+        return;
+      }
+    }
+  }
+  cudaFreeHost(p);
+}
+
+void nd4b_host_trim(void) {
+  std::vector<void*> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_pin.mu);
+    for (auto& kv : g_pin.idle) for (void* q : kv.second) drop.push_back(q);
+    g_pin.idle.clear();
+    g_pin.idle_bytes = 0;
+  }
+  for (void* q : drop) cudaFreeHost(q);
+}
 
 int nd4b_set_chunk_bytes(size_t bytes) {
   Context* ctx;
@@ -589,32 +699,28 @@ int nd4b_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
   const int64_t a_elems = (int64_t)I * K, b_elems = (int64_t)K * J, c_elems = (int64_t)I * J;
   const int nd = (int)ctx->devs.size();
 
-  // Row-panel split of a single large product over the devices (B replicated, A and C split by rows).
+  // Row-panel split of a single large product over the devices: B is replicated, A and C are split by
+  // rows.  The rows are the units of the ordinary sharded pipeline (A rows in, C rows out), so that pageable operands go
+  // through the pinned ring and the devices work concurrently whatever memory the caller passed.
   if (batch == 1 && nd > 1 && I >= 256 * nd) {
-    for (int d = 0; d < nd; d++) {
-      Device& dev = ctx->devs[d];
+    const size_t bb = (size_t)b_elems * 8;
+    for (auto& dev : ctx->devs) {
       CU(cudaSetDevice(dev.id));
-      Slot& slot = dev.slots[0];
-      const int r0 = (int)((int64_t)I * d / nd), r1 = (int)((int64_t)I * (d + 1) / nd);
-      const size_t ab = (size_t)(r1 - r0) * K * 8, bb = (size_t)b_elems * 8, cb = (size_t)(r1 - r0) * J * 8;
-      if (int rc = ensure(slot, 0, ab)) return rc;
-      if (int rc = ensure(slot, 1, bb)) return rc;
-      if (int rc = ensure(slot, 2, cb)) return rc;
-      CU(cudaMemcpyAsync(slot.buf[0], A + (int64_t)r0 * K, ab, cudaMemcpyHostToDevice, slot.stream));
-      CU(cudaMemcpyAsync(slot.buf[1], B, bb, cudaMemcpyHostToDevice, slot.stream));
+      if (int rc = ensure_resident(dev, 1, bb)) return rc;
+      CU(cudaMemcpyAsync(dev.resident[1], B, bb, cudaMemcpyHostToDevice, dev.slots[0].stream));
+      ctx->h2d += bb;
+    }
+    for (auto& dev : ctx->devs) {
+      CU(cudaSetDevice(dev.id));
+      CU(cudaStreamSynchronize(dev.slots[0].stream));
+    }
+    auto launch_rows = [&](const ChunkArgs& a) -> int {
       BatchMap m1;
       memset(&m1, 0, sizeof m1);
-      if (int rc = check_cuda_launch(nd4b::launch_matmul(slot.stream, (const double*)slot.buf[0], (const double*)slot.buf[1],
-                                                         (double*)slot.buf[2], 1, r1 - r0, K, J, m1, dev.sm_count), ctx)) return rc;
-      CU(cudaMemcpyAsync(C + (int64_t)r0 * J, slot.buf[2], cb, cudaMemcpyDeviceToHost, slot.stream));
-      ctx->h2d += ab + bb;
-      ctx->d2h += cb;
-    }
-    for (int d = 0; d < nd; d++) {
-      CU(cudaSetDevice(ctx->devs[d].id));
-      CU(cudaStreamSynchronize(ctx->devs[d].slots[0].stream));
-    }
-    return ND4B_OK;
+      return check_cuda_launch(nd4b::launch_matmul(a.stream, a.in[0], static_cast<const double*>(a.dev->resident[1]), a.out[0], 1,
+                                                   (int)a.count, K, J, m1, a.dev->sm_count), ctx);
+    };
+    return run_pipeline(ctx, I, {{A, nullptr, (int64_t)K}}, {{nullptr, C, (int64_t)J}}, 0, launch_rows);
   }
 
   // Operands that follow C's batch index one-to-one are streamed in chunks; operands with any broadcast
@@ -740,10 +846,8 @@ int nd4b_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t*
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->calls++;
   const long long none = LLONG_MAX;
-  for (auto& d : ctx->devs) {
-    CU(cudaSetDevice(d.id));
-    CU(cudaMemcpy(d.d_info, &none, sizeof none, cudaMemcpyHostToDevice));
-  }
+  for (auto& d : ctx->devs)
+    if (int rc = reset_device_words(d, d.d_info, &none, sizeof none)) return rc;
   const int64_t nn = (int64_t)n * n;
   auto launch = [&](const ChunkArgs& a) -> int {
     return check_cuda_launch(nd4b::launch_cholesky(a.stream, a.in[0], a.out[0], a.count, n, a.dev->d_info, a.base), ctx);
@@ -825,10 +929,9 @@ int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
   if (int rc = get_ctx(&ctx)) return rc;
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->calls++;
-  for (auto& d : ctx->devs) {
-    CU(cudaSetDevice(d.id));
-    CU(cudaMemset(d.d_ints, 0, 4 * sizeof(int)));
-  }
+  const int zeros[4] = {0, 0, 0, 0};
+  for (auto& d : ctx->devs)
+    if (int rc = reset_device_words(d, d.d_ints, zeros, sizeof zeros)) return rc;
   const int L = std::min(rows, cols);
   const size_t work_unit = nd4b::svd_workspace_bytes(1, rows, cols);
   auto launch = [&](const ChunkArgs& a) -> int {
@@ -849,6 +952,194 @@ int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
   ctx->last_sweeps = sweeps;
   if (sweeps_out) *sweeps_out = sweeps;
   if (failed) return fail(ND4B_E_NO_CONVERGENCE, "svd_jac_1sided: no convergence within the sweep limit (NaN or Inf in A?)");
+  return ND4B_OK;
+}
+
+// ---- svd_rank / svd_lstsq / svd_solve (src/la/svd.js:31-226) -------------------------------------
+
+int nd4b_svd_rank_f64(const double* sv, int32_t* rank, int64_t batch, int n) {
+  if (!sv || !rank) return fail(ND4B_E_ARG, "svd_rank: null pointer");
+  if (batch < 1 || n < 1) return fail(ND4B_E_ARG, "svd_rank: batch and n must be >= 1");
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+  // O(batch * n) integer work: one device, one chunk (the call exists so that the rank rule lives behind the boundary)
+  Device& dev = ctx->devs[0];
+  Slot& slot = dev.slots[0];
+  CU(cudaSetDevice(dev.id));
+  const size_t in_bytes = (size_t)batch * n * 8, out_bytes = (size_t)batch * 4;
+  if (int rc = ensure(slot, 0, in_bytes)) return rc;
+  if (int rc = ensure(slot, kOutBase, out_bytes)) return rc;
+  const int zeros[4] = {0, 0, 0, 0};
+  if (int rc = reset_device_words(dev, dev.d_ints, zeros, sizeof zeros)) return rc;
+  CU(cudaMemcpyAsync(slot.buf[0], sv, in_bytes, cudaMemcpyHostToDevice, slot.stream));
+  if (int rc = check_cuda_launch(nd4b::launch_svd_rank(slot.stream, (const double*)slot.buf[0], (int*)slot.buf[kOutBase], batch, n,
+                                                       dev.d_ints + 2), ctx)) { quiesce(ctx); return rc; }
+  int bad = 0;
+  cudaError_t e1 = cudaMemcpyAsync(rank, slot.buf[kOutBase], out_bytes, cudaMemcpyDeviceToHost, slot.stream);
+  cudaError_t e2 = cudaMemcpyAsync(&bad, dev.d_ints + 2, sizeof bad, cudaMemcpyDeviceToHost, slot.stream);
+  cudaError_t e3 = cudaStreamSynchronize(slot.stream);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { quiesce(ctx); return fail(ND4B_E_CUDA, "svd_rank: copy failed"); }
+  ctx->h2d += in_bytes;
+  ctx->d2h += out_bytes;
+  if (bad) return fail(ND4B_E_NAN_INPUT, "svd_rank(): NaN or Infinity encountered.");
+  return ND4B_OK;
+}
+
+namespace {
+struct Operand4 { const int32_t* shape; int ndim; int lead; int64_t elems; const char* name; };
+
+// Validation and broadcast shape of svd_lstsq(U,sv,V,y) with the reference's checks and texts (svd.js:112-147).
+int svd_lstsq_shape_impl(const Operand4 (&op)[4], int32_t* x_shape, int* x_ndim) {
+  static const char* nd_msg[4] = {"svd_lstsq(U,sv,V, y): U.ndim must be at least 2.", "svd_lstsq(U,sv,V, y): sv.ndim must be at least 1.",
+                                  "svd_lstsq(U,sv,V, y): V.ndim must be at least 2.", "svd_lstsq(U,sv,V, y): y.ndim must be at least 2."};
+  for (int o = 0; o < 4; o++) {
+    if (!op[o].shape) return fail(ND4B_E_ARG, "svd_lstsq: null shape");
+    if (op[o].ndim < (o == 1 ? 1 : 2)) return fail(o == 3 ? ND4B_E_B_NDIM : ND4B_E_A_NDIM, "%s", nd_msg[o]);
+    if (op[o].ndim > ND4B_MAX_NDIM - 1) return fail(ND4B_E_ARG, "svd_lstsq: ndim > %d", ND4B_MAX_NDIM - 1);
+    for (int d = 0; d < op[o].ndim; d++) if (op[o].shape[d] < 1) return fail(ND4B_E_ARG, "Invalid shape: dims must be >= 1.");
+  }
+  const int32_t *us = op[0].shape, *ss = op[1].shape, *vs = op[2].shape, *ys = op[3].shape;
+  const int N = us[op[0].ndim - 2], M = us[op[0].ndim - 1], I = vs[op[2].ndim - 1], J = ys[op[3].ndim - 1];
+  if (N != ys[op[3].ndim - 2]) return fail(ND4B_E_INNER, "svd_lstsq(U,sv,V, y): U and y don't match.");
+  if (M != ss[op[1].ndim - 1]) return fail(ND4B_E_INNER, "svd_lstsq(U,sv,V, y): U and sv don't match.");
+  if (M != vs[op[2].ndim - 2]) return fail(ND4B_E_INNER, "svd_lstsq(U,sv,V, y): V and sv don't match.");
+  const int ndim = std::max(std::max(op[0].ndim, op[1].ndim + 1), std::max(op[2].ndim, op[3].ndim));
+  for (int d = 0; d < ndim; d++) x_shape[d] = 1;
+  x_shape[ndim - 2] = I;
+  x_shape[ndim - 1] = J;
+  static const int order[4] = {0, 2, 3, 1};   // U, V, y, then sv (svd.js:132-145)
+  for (int w = 0; w < 4; w++) {
+    const Operand4& a = op[order[w]];
+    for (int i = ndim - 2, j = a.lead; i-- > 0 && j-- > 0;) {
+      if (x_shape[i] == 1) x_shape[i] = a.shape[j];
+      else if (x_shape[i] != a.shape[j] && a.shape[j] != 1)
+        return fail(ND4B_E_BROADCAST, "svd_lstsq(U,sv,V, y): U,sv,V,y not broadcast-compatible.");
+    }
+  }
+  *x_ndim = ndim;
+  return ND4B_OK;
+}
+}  // namespace
+
+int nd4b_svd_lstsq_shape(const int32_t* u_shape, int u_ndim, const int32_t* sv_shape, int sv_ndim,
+                         const int32_t* v_shape, int v_ndim, const int32_t* y_shape, int y_ndim,
+                         int32_t* x_shape, int* x_ndim) {
+  if (!x_shape || !x_ndim) return fail(ND4B_E_ARG, "svd_lstsq_shape: null pointer");
+  const Operand4 op[4] = {{u_shape, u_ndim, u_ndim - 2, 0, "U"}, {sv_shape, sv_ndim, sv_ndim - 1, 0, "sv"},
+                          {v_shape, v_ndim, v_ndim - 2, 0, "V"}, {y_shape, y_ndim, y_ndim - 2, 0, "y"}};
+  return svd_lstsq_shape_impl(op, x_shape, x_ndim);
+}
+
+int nd4b_svd_lstsq_f64(const double* U, const int32_t* u_shape, int u_ndim, const double* sv, const int32_t* sv_shape, int sv_ndim,
+                       const double* V, const int32_t* v_shape, int v_ndim, const double* Y, const int32_t* y_shape, int y_ndim,
+                       double* X, const int32_t* x_shape, int x_ndim) {
+  if (!U || !sv || !V || !Y || !X || !x_shape) return fail(ND4B_E_ARG, "svd_lstsq: null pointer");
+  Operand4 op[4] = {{u_shape, u_ndim, u_ndim - 2, 0, "U"}, {sv_shape, sv_ndim, sv_ndim - 1, 0, "sv"},
+                    {v_shape, v_ndim, v_ndim - 2, 0, "V"}, {y_shape, y_ndim, y_ndim - 2, 0, "y"}};
+  int32_t want[ND4B_MAX_NDIM];
+  int ndim = 0;
+  if (int rc = svd_lstsq_shape_impl(op, want, &ndim)) return rc;
+  if (ndim != x_ndim) return fail(ND4B_E_SHAPE, "svd_lstsq: result ndim %d, expected %d", x_ndim, ndim);
+  for (int d = 0; d < ndim; d++)
+    if (want[d] != x_shape[d]) return fail(ND4B_E_SHAPE, "svd_lstsq: result shape mismatch at dim %d", d);
+  const int N = u_shape[u_ndim - 2], M = u_shape[u_ndim - 1], I = v_shape[v_ndim - 1], J = y_shape[y_ndim - 1];
+  if ((size_t)M * J * 8 > 200 * 1024) return fail(ND4B_E_ARG, "svd_lstsq: M*J = %d*%d exceeds the shared-memory tile of the kernel", M, J);
+  op[0].elems = (int64_t)N * M; op[1].elems = M; op[2].elems = (int64_t)M * I; op[3].elems = (int64_t)N * J;
+  const double* ptr[4] = {U, sv, V, Y};
+
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->calls++;
+
+  // odometer over the result's leading dims: strides per operand (0 = broadcast), adjacent dims merged when all four stay affine
+  const int nb = ndim - 2;
+  std::vector<int64_t> size(nb);
+  std::vector<int64_t> str[4];
+  bool full[4];
+  int64_t count[4];
+  for (int o = 0; o < 4; o++) {
+    str[o].assign(nb, 0);
+    full[o] = true;
+    int64_t s = op[o].elems;
+    for (int d = nb - 1; d >= 0; d--) {
+      const int idx = d - nb + op[o].lead;
+      const int64_t n = idx >= 0 ? op[o].shape[idx] : 1;
+      str[o][d] = n > 1 ? s : 0;
+      if (n != x_shape[d]) full[o] = false;
+      s *= n;
+    }
+    count[o] = s / op[o].elems;
+  }
+  BatchMap4 map;
+  memset(&map, 0, sizeof map);
+  int64_t batch = 1;
+  {
+    std::vector<int64_t> ms;
+    std::vector<int64_t> mstr[4];
+    for (int d = 0; d < nb; d++) {
+      size[d] = x_shape[d];
+      batch *= size[d];
+      if (size[d] == 1) continue;
+      bool merge = !ms.empty();
+      for (int o = 0; o < 4 && merge; o++) merge = mstr[o].back() == size[d] * str[o][d];
+      if (merge) {
+        ms.back() *= size[d];
+        for (int o = 0; o < 4; o++) mstr[o].back() = str[o][d];
+      } else {
+        ms.push_back(size[d]);
+        for (int o = 0; o < 4; o++) mstr[o].push_back(str[o][d]);
+      }
+    }
+    if (ms.size() > 8) return fail(ND4B_E_ARG, "svd_lstsq: more than 8 non-mergeable broadcast dims are not supported");
+    map.nd = (int)ms.size();
+    for (int d = 0; d < map.nd; d++) {
+      map.size[d] = ms[d];
+      for (int o = 0; o < 4; o++) map.str[o][d] = mstr[o][d];
+    }
+  }
+  const int zeros[4] = {0, 0, 0, 0};
+  for (auto& d : ctx->devs)
+    if (int rc = reset_device_words(d, d.d_ints, zeros, sizeof zeros)) return rc;
+  std::vector<Stream1> ins, outs;
+  int slot_of[4] = {-1, -1, -1, -1};
+  for (int o = 0; o < 4; o++)
+    if (full[o]) { slot_of[o] = (int)ins.size(); ins.push_back({ptr[o], nullptr, op[o].elems}); }
+  outs.push_back({nullptr, X, (int64_t)I * J});
+  for (auto& dev : ctx->devs) {
+    CU(cudaSetDevice(dev.id));
+    bool any = false;
+    for (int o = 0; o < 4; o++) {
+      if (full[o]) continue;
+      const size_t bytes = (size_t)count[o] * op[o].elems * 8;
+      if (int rc = ensure_resident(dev, o, bytes)) return rc;
+      CU(cudaMemcpyAsync(dev.resident[o], ptr[o], bytes, cudaMemcpyHostToDevice, dev.slots[0].stream));
+      ctx->h2d += bytes;
+      any = true;
+    }
+    if (any) CU(cudaStreamSynchronize(dev.slots[0].stream));
+  }
+  auto launch = [&](const ChunkArgs& a) -> int {
+    BatchMap4 m = map;
+    m.base = a.base;
+    const double* p[4];
+    for (int o = 0; o < 4; o++) {
+      m.lin[o] = full[o] ? op[o].elems : (count[o] == 1 ? 0 : -1);
+      p[o] = full[o] ? a.in[slot_of[o]] : static_cast<const double*>(a.dev->resident[o]);
+    }
+    return check_cuda_launch(nd4b::launch_svd_lstsq(a.stream, p[0], p[1], p[2], p[3], a.out[0], a.count, N, M, I, J, m, a.dev->d_ints + 2), ctx);
+  };
+  if (int rc = run_pipeline(ctx, batch, ins, outs, 0, launch)) return rc;
+  int bad = 0;
+  for (auto& d : ctx->devs) {
+    int h = 0;
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpy(&h, d.d_ints + 2, sizeof h, cudaMemcpyDeviceToHost));
+    bad |= h;
+  }
+  if (bad) return fail(ND4B_E_NAN_INPUT, "svd_solve(): NaN or Infinity encountered.");
   return ND4B_OK;
 }
 
@@ -1013,6 +1304,18 @@ int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, 
   if (int rc = dev_enter(device, &ctx, &sms)) return rc;
   return check_cuda_launch(nd4b::launch_svd_jac1((cudaStream_t)stream, A, U, sv, V, batch, rows, cols, sweeps, nullptr,
                                                  workspace, workspace_bytes), ctx);
+}
+
+int nd4b_dev_svd_lstsq_f64(int device, void* stream, const double* U, const double* sv, const double* V, const double* Y, double* X,
+                           int64_t batch, int N, int M, int I, int J, int* fail_flag) {
+  if (!U || !sv || !V || !Y || !X || batch < 1 || N < 1 || M < 1 || I < 1 || J < 1 || (size_t)M * J * 8 > 200 * 1024)
+    return fail(ND4B_E_ARG, "dev_svd_lstsq: bad argument");
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  BatchMap4 map;
+  memset(&map, 0, sizeof map);
+  map.lin[0] = (int64_t)N * M; map.lin[1] = M; map.lin[2] = (int64_t)M * I; map.lin[3] = (int64_t)N * J;
+  return check_cuda_launch(nd4b::launch_svd_lstsq((cudaStream_t)stream, U, sv, V, Y, X, batch, N, M, I, J, map, fail_flag), ctx);
 }
 
 int nd4b_dev_svd_sweep_counter(int device, unsigned long long* counter) {

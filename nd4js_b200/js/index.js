@@ -12,6 +12,12 @@ const nd = require('nd4js');
 const addon = require('../addon/build/Release/nd4b.node');
 const {NDArray, asarray} = nd;
 
+// Result storage: large results are page-locked (addon.pinnedFloat64Array -> nd4b_host_alloc, a cached pool), so the D2H
+// copies of the call are DMA'd straight into the array the caller receives and a later nd.la call on it is DMA'd
+// straight out of it; small ones are ordinary typed arrays.
+const PINNED_MIN_LENGTH = (1 << 20) / 8;
+const alloc = n => n >= PINNED_MIN_LENGTH ? addon.pinnedFloat64Array(n) : new Float64Array(n);
+
 function f64(a, who) {
   if (a.dtype === 'float64') return a.data;
   if (a.dtype === 'int32') return Float64Array.from(a.data); // upcast as qr.js:93 / cholesky.js:58 do
@@ -24,7 +30,7 @@ function matmul2(a, b) {
   if (b.ndim < 2) throw new Error('B must be at least 2D.');
   const shape = new Int32Array(Math.max(a.ndim, b.ndim));
   addon.matmulShape(a.shape, b.shape, shape); // throws the reference's texts on mismatch
-  const c = new Float64Array(shape.reduce((m, n) => m * n, 1));
+  const c = alloc(shape.reduce((m, n) => m * n, 1));
   addon.matmul(f64(a, 'matmul2'), a.shape, f64(b, 'matmul2'), b.shape, c, shape);
   return new NDArray(shape, c);
 }
@@ -73,7 +79,7 @@ function matmul(...matrices) {
   product(0, n - 1);
   for (const [i, m] of matrices.entries())
     if (m.ndim < 2) throw new Error(i === 0 ? 'A must be at least 2D.' : 'B must be at least 2D.');
-  const shape = Int32Array.from(op[0][n - 1][1]), c = new Float64Array(shape.reduce((x, y) => x * y, 1));
+  const shape = Int32Array.from(op[0][n - 1][1]), c = alloc(shape.reduce((x, y) => x * y, 1));
   addon.matmulPlan(matrices.map(m => f64(m, 'matmul')), matrices.map(m => Int32Array.from(m.shape)), Int32Array.from(plan), c, shape);
   return new NDArray(shape, c);
 }
@@ -82,7 +88,7 @@ function cholesky_decomp(S) {
   S = asarray(S);
   const [N, M] = S.shape.slice(-2);
   if (N !== M) throw new Error('Last two dimensions must be quadratic.');
-  const s = f64(S, 'cholesky_decomp'), L = new Float64Array(s.length);
+  const s = f64(S, 'cholesky_decomp'), L = alloc(s.length);
   addon.cholesky(s, L, s.length / (N * N), N); // throws 'Matrix contains NaNs or is (near) singular.'
   return new NDArray(S.shape, L);
 }
@@ -93,7 +99,7 @@ function qr_decomp(A) {
   const [N, M] = A.shape.slice(-2), L = Math.min(N, M), a = f64(A, 'qr_decomp'), batch = a.length / (N * M);
   const qShape = Int32Array.from(A.shape), rShape = Int32Array.from(A.shape);
   qShape[qShape.length - 1] = L; rShape[rShape.length - 2] = L;
-  const Q = new Float64Array(batch * N * L), R = new Float64Array(batch * L * M);
+  const Q = alloc(batch * N * L), R = alloc(batch * L * M);
   addon.qr(a, Q, R, batch, N, M);
   return [new NDArray(qShape, Q), new NDArray(rShape, R)];
 }
@@ -116,7 +122,7 @@ function svd_jac_1sided(A) {
   const [N, M] = A.shape.slice(-2), L = Math.min(N, M), a = f64(A, 'svd_jac_1sided'), batch = a.length / (N * M);
   const uShape = Int32Array.from(A.shape), vShape = Int32Array.from(A.shape), sShape = A.shape.slice(0, -1);
   uShape[uShape.length - 1] = L; vShape[vShape.length - 2] = L; sShape[sShape.length - 1] = L;
-  const U = new Float64Array(batch * N * L), sv = new Float64Array(batch * L), V = new Float64Array(batch * L * M);
+  const U = alloc(batch * N * L), sv = alloc(batch * L), V = alloc(batch * L * M);
   addon.svdJac1(a, U, sv, V, batch, N, M);
   return [new NDArray(uShape, U), new NDArray(sShape, sv), new NDArray(vShape, V)];
 }
@@ -130,7 +136,7 @@ function triSolve(op, T, Y, errT, errY) {
   for (const shp of [T.shape, Y.shape])
     for (let i = ndim - 2, j = shp.length - 2; i-- > 0 && j-- > 0;)
       if (xShape[i] === 1) xShape[i] = shp[j];   // a mismatch is reported by the library with the reference's text
-  const X = new Float64Array(xShape.reduce((a, b) => a * b, 1));
+  const X = alloc(xShape.reduce((a, b) => a * b, 1));
   addon.triSolve(op, f64(T, 'tri_solve'), T.shape, f64(Y, 'tri_solve'), Y.shape, X, xShape);
   return new NDArray(xShape, X);
 }
@@ -152,7 +158,7 @@ function qr_lstsq(Q, R, y) {
   const lead = a => Array.from(a.shape.slice(0, -2)).join(), sameBatch = lead(Q) === lead(R) && lead(Q) === lead(y);
   if (M <= 32 && I <= 32 && sameBatch) {
     const xShape = Int32Array.from([...Q.shape.slice(0, -2), I, J]), q = f64(Q, 'qr_lstsq'), batch = q.length / (N * M);
-    const X = new Float64Array(batch * I * J);
+    const X = alloc(batch * I * J);
     addon.qrLstsq(q, f64(R, 'qr_lstsq'), f64(y, 'qr_lstsq'), X, batch, N, M, I, J);
     return new NDArray(xShape, X);
   }
@@ -173,6 +179,39 @@ function qr_lstsq(Q, R, y) {
   return new NDArray(xShape, X);
 }
 
-module.exports = {qr_lstsq, matmul2, matmul, cholesky_decomp, qr_decomp, _qr_decomp_inplace, svd_jac_1sided, tril_solve, triu_solve, cholesky_solve,
+// svd_rank / svd_lstsq / svd_solve (svd.js:31-226): the rank rule and the fused solve run on the device
+function svd_rank(sv) {
+  sv = asarray(sv);
+  const N = sv.shape[sv.ndim - 1], rShape = sv.shape.slice(0, -1), d = f64(sv, 'svd_rank'), r = new Int32Array(d.length / N);
+  addon.svdRank(d, r, N);   // throws 'svd_rank(): NaN or Infinity encountered.'
+  return new NDArray(rShape, r);
+}
+
+function svd_lstsq(U, sv, V, y) {
+  if (y == undefined) {
+    if (V != undefined) throw new Error('svd_lstsq(Q,R,P, y): Either 2 ([Q,R,P], y) or 4 arguments (Q,R,P, y) expected.');
+    y = sv; [U, sv, V] = U;
+  }
+  U = asarray(U); sv = asarray(sv); V = asarray(V); y = asarray(y);
+  const xShapeMax = new Int32Array(Math.max(U.ndim, sv.ndim + 1, V.ndim, y.ndim, 2));
+  const ndim = addon.svdLstsqShape(U.shape, sv.shape, V.shape, y.shape, xShapeMax);   // throws the reference's texts
+  const xShape = xShapeMax.slice(0, ndim), X = alloc(xShape.reduce((a, b) => a * b, 1));
+  addon.svdLstsq(f64(U, 'svd_lstsq'), U.shape, f64(sv, 'svd_lstsq'), sv.shape, f64(V, 'svd_lstsq'), V.shape, f64(y, 'svd_lstsq'), y.shape, X, xShape);
+  return new NDArray(xShape, X);
+}
+
+// The reference's singularity scan (svd.js:87-95) starts from an undefined loop variable and never runs: svd_solve returns
+// the least-squares solution for every square system.
+function svd_solve(U, sv, V, y) {
+  if (y == undefined) {
+    if (V != undefined) throw new Error('svd_lstsq(Q,R,P, y): Either 2 ([Q,R,P], y) or 4 arguments (Q,R,P, y) expected.');
+    y = sv; [U, sv, V] = U;
+  }
+  U = asarray(U); sv = asarray(sv); V = asarray(V);
+  if (U.shape[U.ndim - 2] !== V.shape[V.ndim - 1]) throw new Error('rrqr_solve(Q,R,P, y): System not square.');
+  return svd_lstsq(U, sv, V, y);
+}
+
+module.exports = {svd_rank, svd_lstsq, svd_solve, qr_lstsq, matmul2, matmul, cholesky_decomp, qr_decomp, _qr_decomp_inplace, svd_jac_1sided, tril_solve, triu_solve, cholesky_solve,
                   init: d => addon.init(Int32Array.from(d || [])), stats: addon.stats,
                   pinnedFloat64Array: addon.pinnedFloat64Array};

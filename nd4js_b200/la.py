@@ -33,7 +33,10 @@ def _f64(nd, who):
 
 
 def _new(shape):
-    return np.empty(int(np.prod(shape, dtype=np.int64)), np.float64)
+    """Storage of a result NDArray.  Large results live in page-locked memory from the library's cache (nd4b_host_alloc),
+    so that the D2H copies of the call are DMA'd straight into them and a later nd.la call on the result is DMA'd straight
+    out of them; the block goes back to the cache when the array is garbage collected."""
+    return _lib.pinned_empty(int(np.prod(shape, dtype=np.int64)))
 
 
 def matmul2(a, b):
@@ -293,69 +296,62 @@ def qr_lstsq(Q, R, y=None):
     return NDArray(np.asarray(x.shape, np.int32), x.reshape(-1))
 
 
-_SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))
-
-
 def svd_rank(sv):
-    """Numerical rank per matrix: number of leading singular values > sqrt(eps)*sv[0] (svd.js:31-58)."""
+    """Numerical rank per matrix: index of the first singular value <= sqrt(eps)*|sv[0]| (svd.js:31-58), computed on the
+    device (nd4b_svd_rank_f64).  Result shape sv.shape[:-1] (int32); like the reference, a non-finite entry raises only
+    when the scan meets it before the cut."""
     sv = asarray(sv)
-    d = sv.numpy().astype(np.float64, copy=False)
-    if not np.isfinite(d).all():
-        raise ValueError("svd_rank(): NaN or Infinity encountered.")
-    t = _SQRT_EPS * np.abs(d[..., :1])
-    below = np.abs(d) <= t
-    r = np.where(below.any(axis=-1), below.argmax(axis=-1), d.shape[-1]).astype(np.int32)
-    shape = np.asarray(d.shape[:-1] if d.ndim > 1 else (1,), np.int32)
-    return NDArray(shape, np.ascontiguousarray(r).reshape(-1))
+    if sv.ndim < 1:
+        raise ValueError("svd_rank(sv): sv.ndim must be at least 1.")
+    n = int(sv.shape[-1])
+    d = _f64(sv, "svd_rank")
+    batch = d.size // n
+    r = np.zeros(batch, np.int32)
+    rc = _lib.load().nd4b_svd_rank_f64(_ptr(d), _ptr(r), batch, n)
+    if rc == _lib.E_NAN_INPUT:
+        raise ValueError(_lib.last_error())
+    _lib.check(rc)
+    return NDArray(np.array(sv.shape[:-1], np.int32), r)   # a 1-D sv gives the 0-d NDArray of the reference (shape [])
 
 
 def svd_lstsq(U, sv=None, V=None, y=None):
-    """x = V^T diag(1/sv[:rank]) U^T y (svd.js:103-226): two GPU matmuls around a host-side scaling of the
-    [M,J] intermediate; the rank cut is the reference's."""
+    """x = V^T diag(1/sv[:rank]) U^T y with the reference's rank cut and broadcasting (svd.js:103-226): one fused kernel
+    behind nd4b_svd_lstsq_f64, bit-identical with the reference's loops."""
     if y is None:
         if V is not None:
             raise ValueError("svd_lstsq(Q,R,P, y): Either 2 ([Q,R,P], y) or 4 arguments (Q,R,P, y) expected.")
         y = sv
         U, sv, V = U
     U, sv, V, y = asarray(U), asarray(sv), asarray(V), asarray(y)
-    if U.ndim < 2:
-        raise ValueError("svd_lstsq(U,sv,V, y): U.ndim must be at least 2.")
-    if sv.ndim < 1:
-        raise ValueError("svd_lstsq(U,sv,V, y): sv.ndim must be at least 1.")
-    if V.ndim < 2:
-        raise ValueError("svd_lstsq(U,sv,V, y): V.ndim must be at least 2.")
-    if y.ndim < 2:
-        raise ValueError("svd_lstsq(U,sv,V, y): y.ndim must be at least 2.")
-    n, m = int(U.shape[-2]), int(U.shape[-1])
-    if n != int(y.shape[-2]):
-        raise ValueError("svd_lstsq(U,sv,V, y): U and y don't match.")
-    if m != int(sv.shape[-1]):
-        raise ValueError("svd_lstsq(U,sv,V, y): U and sv don't match.")
-    if m != int(V.shape[-2]):
-        raise ValueError("svd_lstsq(U,sv,V, y): V and sv don't match.")
-    s = sv.numpy().astype(np.float64, copy=False)
-    try:
-        np.broadcast_shapes(tuple(U.shape[:-2]), tuple(V.shape[:-2]), tuple(y.shape[:-2]), s.shape[:-1])
-    except ValueError:
-        raise ValueError("svd_lstsq(U,sv,V, y): U,sv,V,y not broadcast-compatible.")
-    if not np.isfinite(s).all():
-        raise ValueError("svd_solve(): NaN or Infinity encountered.")
-    rank = svd_rank(sv).numpy().reshape(s.shape[:-1]) if s.ndim > 1 else svd_rank(sv).numpy().reshape(())
-    keep = np.arange(m) < np.asarray(rank)[..., None]
-    inv = np.where(keep, 1.0 / np.where(keep, s, 1.0), 0.0)
-    tmp = matmul2(U.T, y).numpy() * inv[..., :, None]          # diag(1/sv) U^T y, zero beyond the rank
-    return matmul2(V.T, np.ascontiguousarray(tmp))
+    L = _lib.load()
+    shp = [np.ascontiguousarray(a.shape, np.int32) for a in (U, sv, V, y)]
+    x_s = np.zeros(max(U.ndim, sv.ndim + 1, V.ndim, y.ndim, 2), np.int32)
+    nd = C.c_int(0)
+    rc = L.nd4b_svd_lstsq_shape(_ptr(shp[0]), U.ndim, _ptr(shp[1]), sv.ndim, _ptr(shp[2]), V.ndim, _ptr(shp[3]), y.ndim,
+                                _ptr(x_s), C.byref(nd))
+    if rc:
+        raise ValueError(_lib.last_error())
+    x_s = np.ascontiguousarray(x_s[: nd.value])
+    ud, sd, vd, yd = (_f64(a, "svd_lstsq") for a in (U, sv, V, y))
+    x = _new(x_s)
+    rc = L.nd4b_svd_lstsq_f64(_ptr(ud), _ptr(shp[0]), U.ndim, _ptr(sd), _ptr(shp[1]), sv.ndim, _ptr(vd), _ptr(shp[2]), V.ndim,
+                              _ptr(yd), _ptr(shp[3]), y.ndim, _ptr(x), _ptr(x_s), nd.value)
+    if rc == _lib.E_NAN_INPUT:
+        raise ValueError(_lib.last_error())
+    _lib.check(rc)
+    return NDArray(x_s, x)
 
 
 def svd_solve(U, sv=None, V=None, y=None):
-    """svd_lstsq for square systems; raises when a matrix is numerically singular (svd.js:61-100)."""
+    """svd_lstsq for square systems (svd.js:61-100).  The reference means to throw SingularMatrixSolveError for a
+    rank-deficient system, but its scan `for( let r; r < N; r++ )` starts from an undefined r and never runs, so it
+    returns the least-squares solution for every input; this mirror does the same."""
     if y is None:
+        if V is not None:
+            raise ValueError("svd_lstsq(Q,R,P, y): Either 2 ([Q,R,P], y) or 4 arguments (Q,R,P, y) expected.")
         y = sv
         U, sv, V = U
     U, sv, V = asarray(U), asarray(sv), asarray(V)
     if int(U.shape[-2]) != int(V.shape[-1]):
         raise ValueError("rrqr_solve(Q,R,P, y): System not square.")
-    x = svd_lstsq(U, sv, V, y)
-    if (svd_rank(sv).numpy() < int(sv.shape[-1])).any():
-        raise np.linalg.LinAlgError("svd_solve(): singular matrix (SingularMatrixSolveError in the reference)")
-    return x
+    return svd_lstsq(U, sv, V, y)

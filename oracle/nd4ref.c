@@ -565,3 +565,120 @@ double nd4ref_frobenius(const double* x, int64_t n) {
   }
   return isfinite(max) ? sqrt(sum) * max : max;
 }
+
+/* ------------------------------------------------------- svd_rank / svd_lstsq ----- */
+
+#define ND4REF_SQRT_EPS 1.4901161193847656e-08 /* Math.sqrt(Number.EPSILON) = 2^-26 */
+
+/* src/la/svd.js:31-58 — rank[b] = index of the first |sv_r| <= sqrt(eps)*|sv_0|; a non-finite entry met before that throws */
+int nd4ref_svd_rank_f64(const double* sv, int32_t* rank, int64_t batch, int n) {
+  for (int64_t off = 0; off < batch; off++) {
+    const double T = ND4REF_SQRT_EPS * fabs(sv[n * off]);
+    int r = 0;
+    for (; r < n; r++) {
+      const double sv_r = fabs(sv[n * off + r]);
+      if (!isfinite(sv_r)) return ND4REF_E_NAN_INPUT;
+      if (sv_r <= T) break;
+    }
+    rank[off] = r;
+  }
+  return ND4REF_OK;
+}
+
+/* src/la/svd.js:103-226 — U[...,N,M], sv[...,M], V[...,M,I], y[...,N,J] -> x[...,I,J] (shape checked by the caller's wrapper
+ * against nd4ref_svd_lstsq_shape).  The recursion `solv(d)` with its rewinding offsets (:154-222) is restated as an
+ * odometer over the result's leading dims with stride 0 for broadcast dims, which visits the same operand slices. */
+int nd4ref_svd_lstsq_shape(const int32_t* u_shape, int u_ndim, const int32_t* sv_shape, int sv_ndim,
+                           const int32_t* v_shape, int v_ndim, const int32_t* y_shape, int y_ndim,
+                           int32_t* x_shape, int* x_ndim) {
+  if (u_ndim < 2) return ND4REF_E_A_NDIM;
+  if (sv_ndim < 1) return ND4REF_E_A_NDIM;
+  if (v_ndim < 2) return ND4REF_E_A_NDIM;
+  if (y_ndim < 2) return ND4REF_E_B_NDIM;
+  const int N = u_shape[u_ndim - 2], M = u_shape[u_ndim - 1], I = v_shape[v_ndim - 1], J = y_shape[y_ndim - 1];
+  if (N != y_shape[y_ndim - 2]) return ND4REF_E_INNER;
+  if (M != sv_shape[sv_ndim - 1]) return ND4REF_E_INNER;
+  if (M != v_shape[v_ndim - 2]) return ND4REF_E_INNER;
+  int ndim = u_ndim;
+  if (sv_ndim + 1 > ndim) ndim = sv_ndim + 1;
+  if (v_ndim > ndim) ndim = v_ndim;
+  if (y_ndim > ndim) ndim = y_ndim;
+  for (int d = 0; d < ndim; d++) x_shape[d] = 1;
+  x_shape[ndim - 2] = I;
+  x_shape[ndim - 1] = J;
+  const int32_t* shp[4] = {u_shape, v_shape, y_shape, sv_shape};
+  const int lead[4] = {u_ndim - 2, v_ndim - 2, y_ndim - 2, sv_ndim - 1};
+  for (int w = 0; w < 4; w++)
+    for (int i = ndim - 2, j = lead[w]; i-- > 0 && j-- > 0;) {
+      if (x_shape[i] == 1) x_shape[i] = shp[w][j];
+      else if (x_shape[i] != shp[w][j] && shp[w][j] != 1) return ND4REF_E_BROADCAST;
+    }
+  *x_ndim = ndim;
+  return ND4REF_OK;
+}
+
+int nd4ref_svd_lstsq_f64(const double* U, const int32_t* u_shape, int u_ndim, const double* sv, const int32_t* sv_shape, int sv_ndim,
+                         const double* V, const int32_t* v_shape, int v_ndim, const double* Y, const int32_t* y_shape, int y_ndim,
+                         double* X, const int32_t* x_shape, int x_ndim) {
+  int32_t want[64];
+  int ndim = 0;
+  const int rc = nd4ref_svd_lstsq_shape(u_shape, u_ndim, sv_shape, sv_ndim, v_shape, v_ndim, y_shape, y_ndim, want, &ndim);
+  if (rc) return rc;
+  if (ndim != x_ndim) return ND4REF_E_SHAPE;
+  for (int d = 0; d < ndim; d++)
+    if (want[d] != x_shape[d]) return ND4REF_E_SHAPE;
+  const int N = u_shape[u_ndim - 2], M = u_shape[u_ndim - 1], I = v_shape[v_ndim - 1], J = y_shape[y_ndim - 1];
+  const int nb = ndim - 2;
+  const int32_t* shp[4] = {u_shape, sv_shape, v_shape, y_shape};
+  const int lead[4] = {u_ndim - 2, sv_ndim - 1, v_ndim - 2, y_ndim - 2};
+  const int64_t elems[4] = {(int64_t)N * M, M, (int64_t)M * I, (int64_t)N * J};
+  int64_t str[4][64], idx[64], total = 1;
+  for (int o = 0; o < 4; o++) {
+    int64_t s = elems[o];
+    for (int d = nb - 1; d >= 0; d--) {
+      const int k = d - nb + lead[o];
+      const int64_t n = k >= 0 ? shp[o][k] : 1;
+      str[o][d] = n > 1 ? s : 0;
+      s *= n;
+    }
+  }
+  for (int d = 0; d < nb; d++) { idx[d] = 0; total *= x_shape[d]; }
+  double* tmp = (double*)malloc(sizeof(double) * (size_t)M * J);
+  if (!tmp) return ND4REF_E_SHAPE;
+  memset(X, 0, sizeof(double) * (size_t)total * I * J);   /* new DTypeArray(...) is zero-filled, svd.js:151 */
+  for (int64_t m = 0; m < total; m++) {
+    int64_t off[4] = {0, 0, 0, 0};
+    for (int o = 0; o < 4; o++)
+      for (int d = 0; d < nb; d++) off[o] += idx[d] * str[o][d];
+    const double *u = U + off[0], *s = sv + off[1], *v = V + off[2], *y = Y + off[3];
+    double* x = X + m * (int64_t)I * J;
+    /* rank cut, svd.js:163-174 */
+    int R = M;
+    {
+      const double T = ND4REF_SQRT_EPS * fabs(s[0]);
+      for (int r = 0; r < M; r++) {
+        const double sv_r = fabs(s[r]);
+        if (!isfinite(sv_r)) { free(tmp); return ND4REF_E_NAN_INPUT; }
+        if (sv_r <= T) { R = r; break; }
+      }
+    }
+    /* tmp = U.T @ y, svd.js:180-184 */
+    for (int e = 0; e < M * J; e++) tmp[e] = 0.0;
+    for (int k = 0; k < N; k++)
+      for (int i = 0; i < R; i++)
+        for (int j = 0; j < J; j++) tmp[J * i + j] += u[(int64_t)M * k + i] * y[(int64_t)J * k + j];
+    /* tmp \= diag(sv), svd.js:186-189 */
+    for (int i = 0; i < R; i++)
+      for (int j = 0; j < J; j++) tmp[J * i + j] /= s[i];
+    /* x = V.T @ tmp, svd.js:191-195 */
+    for (int k = 0; k < R; k++)
+      for (int i = 0; i < I; i++)
+        for (int j = 0; j < J; j++) x[J * i + j] += v[(int64_t)I * k + i] * tmp[J * k + j];
+    for (int d = nb - 1; d >= 0; d--) {
+      if (++idx[d] < x_shape[d]) break;
+      idx[d] = 0;
+    }
+  }
+  free(tmp);
+  return ND4REF_OK;
+}

@@ -71,6 +71,17 @@ int nd4ref_tri_solve_f64(int op, const double* T, const int32_t* t_shape, int t_
                          const double* Y, const int32_t* y_shape, int y_ndim,
                          double* X, const int32_t* x_shape, int x_ndim);
 
+/* svd_rank (src/la/svd.js:31-58): rank[batch] int32.  svd_lstsq (src/la/svd.js:103-226): x = V^T diag(1/sv[:R]) U^T y with
+ * the rank cut R, four independently broadcast operands; returns ND4REF_E_NAN_INPUT where the reference throws
+ * 'svd_solve(): NaN or Infinity encountered.' / 'svd_rank(): NaN or Infinity encountered.' */
+int nd4ref_svd_rank_f64(const double* sv, int32_t* rank, int64_t batch, int n);
+int nd4ref_svd_lstsq_shape(const int32_t* u_shape, int u_ndim, const int32_t* sv_shape, int sv_ndim,
+                           const int32_t* v_shape, int v_ndim, const int32_t* y_shape, int y_ndim,
+                           int32_t* x_shape, int* x_ndim);
+int nd4ref_svd_lstsq_f64(const double* U, const int32_t* u_shape, int u_ndim, const double* sv, const int32_t* sv_shape, int sv_ndim,
+                         const double* V, const int32_t* v_shape, int v_ndim, const double* Y, const int32_t* y_shape, int y_ndim,
+                         double* X, const int32_t* x_shape, int x_ndim);
+
 /* scalar helpers exposed for unit tests */
 void nd4ref_giv_rot_qr(double a, double b, double out_c_s_norm[3]);      /* _giv_rot.js:22-37   */
 void nd4ref_svd_jac_angles(double Spp, double Spq, double Sqp, double Sqq,

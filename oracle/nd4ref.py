@@ -51,6 +51,12 @@ def lib():
         L.nd4ref_svd_jac2_f64.argtypes = [dp, dp, dp, dp, i64, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.nd4ref_tri_solve_f64.argtypes = [C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int]
         L.nd4ref_tri_solve_f64.restype = C.c_int
+        L.nd4ref_svd_rank_f64.argtypes = [dp, ip, i64, C.c_int]
+        L.nd4ref_svd_rank_f64.restype = C.c_int
+        L.nd4ref_svd_lstsq_shape.argtypes = [ip, C.c_int, ip, C.c_int, ip, C.c_int, ip, C.c_int, ip, C.POINTER(C.c_int)]
+        L.nd4ref_svd_lstsq_shape.restype = C.c_int
+        L.nd4ref_svd_lstsq_f64.argtypes = [dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int]
+        L.nd4ref_svd_lstsq_f64.restype = C.c_int
         L.nd4ref_giv_rot_qr.argtypes = [C.c_double, C.c_double, dp]
         L.nd4ref_svd_jac_angles.argtypes = [C.c_double] * 4 + [dp]
         L.nd4ref_frobenius.argtypes = [dp, i64]
@@ -192,6 +198,35 @@ def qr_lstsq(q, r, y):
         for k in range(n):  # x[i][j] += Q[k][i] * y[k][j], k ascending (qr.js:246-249)
             qy += qb[ix][k, :l, None] * yb[ix][k][None, :]
         x[ix][:l] = _tri_solve(1, np.ascontiguousarray(rb[ix][:l, :l]), qy)
+    return x
+
+
+def svd_rank(sv):
+    """src/la/svd.js:31-58; result shape sv.shape[:-1] (a 1-D sv gives shape ())."""
+    sv = _f64(sv)
+    n = sv.shape[-1]
+    r = np.zeros(sv.shape[:-1], np.int32)
+    rc = lib().nd4ref_svd_rank_f64(_dp(sv), r.ctypes.data_as(C.POINTER(C.c_int32)), sv.size // n, n)
+    if rc:
+        raise RefError(rc)
+    return r
+
+
+def svd_lstsq(u, sv, v, y):
+    """src/la/svd.js:103-226."""
+    u, sv, v, y = _f64(u), _f64(sv), _f64(v), _f64(y)
+    shp = [np.asarray(a.shape, np.int32) for a in (u, sv, v, y)]
+    xs = np.zeros(max(u.ndim, sv.ndim + 1, v.ndim, y.ndim, 2), np.int32)
+    nd = C.c_int(0)
+    rc = lib().nd4ref_svd_lstsq_shape(_ip(shp[0]), u.ndim, _ip(shp[1]), sv.ndim, _ip(shp[2]), v.ndim, _ip(shp[3]), y.ndim, _ip(xs), C.byref(nd))
+    if rc:
+        raise RefError(rc)
+    x = np.empty(tuple(int(t) for t in xs[: nd.value]))
+    xs = np.asarray(x.shape, np.int32)
+    rc = lib().nd4ref_svd_lstsq_f64(_dp(u), _ip(shp[0]), u.ndim, _dp(sv), _ip(shp[1]), sv.ndim, _dp(v), _ip(shp[2]), v.ndim,
+                                    _dp(y), _ip(shp[3]), y.ndim, _dp(x), _ip(xs), x.ndim)
+    if rc:
+        raise RefError(rc)
     return x
 
 

@@ -1,5 +1,8 @@
-"""Multi-GPU path on real devices: the batch sharded over one process per GPU, results gathered with NCCL.
-Needs two visible GPUs; on a one-GPU box the world_size-2 logic is covered by the gloo test in test_host_logic.py."""
+"""Multi-GPU paths on real devices; every test skips on a box with fewer than two GPUs.
+  * one process, one context over several devices (nd.init([0,1])): shards, replicated broadcast operands, the row-panel split
+    of a single large matmul and the global cholesky failure index — bit-for-bit against the one-device context;
+  * one process per GPU with the results gathered by NCCL (the C5 configuration of BASELINE.json).
+On a one-GPU box the world_size-2 logic is covered by the gloo test in test_host_logic.py."""
 import json
 import os
 import subprocess
@@ -11,9 +14,24 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_sharded_svd_with_nccl_gather_matches_unsharded():
+def _gpus():
     import torch
-    if torch.cuda.device_count() < 2:
+    return torch.cuda.device_count()
+
+
+def test_multi_device_context_matches_one_device_bit_for_bit():
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "multidev_check.py"), "2"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_devices"] == 2
+    assert line["all_equal"], line
+
+
+def test_sharded_svd_with_nccl_gather_matches_unsharded():
+    if _gpus() < 2:
         pytest.skip("needs two GPUs")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29571",

@@ -242,3 +242,23 @@ def test_qr_decomp_inplace_restatement(ref, shape):
     k = min(m, n)
     _, r2 = ref.qr_decomp(a)
     np.testing.assert_allclose(np.abs(r[..., :k, :]), np.abs(r2), atol=1e-13)
+
+
+def test_svd_rank_and_lstsq_restatement(ref):
+    """src/la/svd.js:31-58 and :103-226 against LAPACK (minimum-norm least squares with the same rank cut), incl. broadcasting."""
+    rng = np.random.default_rng(5)
+    a, y = rng.uniform(-1, 1, (4, 9, 6)), rng.uniform(-1, 1, (4, 9, 2))
+    a[1, :, 5] = a[1, :, 0]                       # rank 5
+    u, s, vt = np.linalg.svd(a, full_matrices=False)
+    assert list(ref.svd_rank(s)) == [6, 5, 6, 6]
+    x = ref.svd_lstsq(u, s, vt, y)
+    for b in range(4):
+        np.testing.assert_allclose(x[b], np.linalg.lstsq(a[b], y[b], rcond=1e-8)[0], atol=1e-12)
+    # operands broadcast independently: one factorisation, many right-hand sides and the other way round
+    yb = rng.uniform(-1, 1, (3, 1, 9, 2))
+    xb = ref.svd_lstsq(u, s, vt, yb)
+    assert xb.shape == (3, 4, 6, 2)
+    np.testing.assert_array_equal(xb[2, 1], ref.svd_lstsq(u[1], s[1], vt[1], yb[2, 0]))
+    assert ref.svd_rank(np.array([3.0, 1e-9, np.nan])).shape == () and int(ref.svd_rank(np.array([3.0, 1e-9, np.nan]))) == 1
+    with pytest.raises(ref.RefError):
+        ref.svd_rank(np.array([3.0, np.inf, 1.0]))
