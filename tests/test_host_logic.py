@@ -136,9 +136,16 @@ def test_two_rank_gloo_sharding_reassembles_the_reference_result(ref, tmp_path):
     assert "OK" in out.stdout
 
 
-def test_svd_rank_host_logic():
-    from nd4js_b200 import la
-    sv = np.array([[3.0, 1.0, 1e-9, 0.0], [2.0, 1.0, 0.5, 0.25], [0.0, 0.0, 0.0, 0.0]])
-    assert list(la.svd_rank(sv).numpy()) == [2, 4, 0]   # cut at sqrt(eps)*sv[0], svd.js:31-58
-    with pytest.raises(ValueError, match="NaN or Infinity"):
-        la.svd_rank(np.array([1.0, np.nan]))
+def test_svd_rank_and_lstsq_have_no_cpu_path():
+    """svd_rank / svd_lstsq run behind the C ABI on the device (src/la/svd.js:31-226): without a usable GPU they fail loudly —
+    argument errors with the reference's texts are still raised first, on the host."""
+    import torch
+    from nd4js_b200 import Nd4bError, la
+    with pytest.raises(ValueError, match="U and y don't match"):
+        la.svd_lstsq(np.eye(3), np.ones(3), np.eye(3), np.ones((4, 1)))
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the device path is covered by the -m gpu tests")
+    with pytest.raises(Nd4bError, match="no usable CUDA device|no CPU fallback"):
+        la.svd_rank(np.array([[3.0, 1.0, 1e-9, 0.0]]))
+    with pytest.raises(Nd4bError, match="no usable CUDA device|no CPU fallback"):
+        la.svd_lstsq(np.eye(3), np.ones(3), np.eye(3), np.ones((3, 1)))
