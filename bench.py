@@ -245,7 +245,7 @@ class DeviceCase:
             self.info = torch.full((1,), 2 ** 62, dtype=torch.int64, device="cuda")
         elif name == "s3":
             gmat = u(units, 16, 16)
-            low = torch.linalg.cholesky(torch.baddbmm(16.0 * torch.eye(16, **f64).expand(units, 16, 16), gmat, gmat.transpose(1, 2)))
+            low = torch.linalg.cholesky(torch.baddbmm(16.0 * torch.eye(16, **f64).expand(units, 16, 16), gmat, gmat.transpose(1, 2))).contiguous()  # row-major
             del gmat
             self.ins, self.out = [low, u(units, 16, 1)], [torch.empty(units, 16, 1, **f64)]
         elif name == "l4":

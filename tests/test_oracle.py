@@ -262,3 +262,71 @@ def test_svd_rank_and_lstsq_restatement(ref):
     assert ref.svd_rank(np.array([3.0, 1e-9, np.nan])).shape == () and int(ref.svd_rank(np.array([3.0, 1e-9, np.nan]))) == 1
     with pytest.raises(ref.RefError):
         ref.svd_rank(np.array([3.0, np.inf, 1.0]))
+
+
+# ------------------------------------------------------------ second mirror, seeded reference generators ----
+
+def test_alea_known_answers():
+    """The restated AleaRNG (src/rand/alea_rng.js:37-142) against the published vectors of the Alea generator it is
+    (seedrandom's alea('hello.'): next, 53-bit double, int32)."""
+    from oracle.alea import DIV53, AleaRNG, _i32, mash
+    r = AleaRNG("hello.")
+    assert r._next() == 0.4783254903741181
+    assert r._next() + _i32(r._next() * 0x200000) * DIV53 == 0.8297006866124559
+    assert _i32(r._next() * 4294967296.0) == 1076136327
+    assert mash(" ", 0xefc8249d) == mash(" ", 0xefc8249d) and mash("ab", 1.0) != mash("ba", 1.0)
+    u = AleaRNG(7)
+    xs = [u.uniform(-4, 4) for _ in range(1000)]
+    assert -4 <= min(xs) and max(xs) < 4 and abs(sum(xs) / 1000) < 0.4
+    ks = [u.int(1, 4) for _ in range(300)]
+    assert set(ks) == {1, 2, 3}
+    q = u.ortho(3, 7, 4)
+    assert np.max(np.abs(np.swapaxes(q, -1, -2) @ q - np.eye(4))) < 1e-14
+
+
+@pytest.mark.parametrize("shape", [(3, 9, 5), (2, 5, 9), (4, 6, 6), (2, 1, 1), (1, 17, 17), (2, 20, 3), (1, 12, 30), (1, 64, 32),
+                                   (1, 1, 7), (1, 7, 1), (2, 3, 8, 8)])
+def test_numpy_mirror_of_qr_is_bit_identical_with_the_c_oracle(ref, shape):
+    import ref_mirror
+    a = uniform(900 + sum(shape), shape)
+    if shape[-1] > 2:
+        a.reshape(-1, *shape[-2:])[0, :, 1] = 0.0       # a zero column: the `continue` branches
+    q1, r1 = ref_mirror.qr_decomp(a)
+    q2, r2 = ref.qr_decomp(a)
+    assert q1.shape == q2.shape and r1.shape == r2.shape
+    assert (q1.view(np.int64) == q2.view(np.int64)).all() and (r1.view(np.int64) == r2.view(np.int64)).all()
+
+
+@pytest.mark.parametrize("shape", [(3, 6, 6), (2, 9, 5), (2, 5, 9), (2, 1, 1), (1, 17, 17), (1, 2, 2), (1, 1, 4), (1, 4, 1), (1, 33, 20),
+                                   (1, 40, 40)])
+def test_numpy_mirror_of_svd_jac_2sided_is_bit_identical_with_the_c_oracle(ref, shape):
+    import ref_mirror
+    a = uniform(950 + sum(shape), shape)
+    if min(shape[-2:]) > 2:
+        a[0, :, 1] = a[0, :, 0]                           # rank deficient: zero singular values, sign flips of -0
+    got = ref_mirror.svd_jac_2sided(a)
+    want = ref.svd_jac_2sided(a)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and (np.ascontiguousarray(g).view(np.int64) == np.ascontiguousarray(w).view(np.int64)).all()
+
+
+def test_oracle_passes_the_reference_svd_suites_on_the_reference_inputs(ref):
+    """The restated svd_jac_2sided on the items the reference's own suites generate (same seeds, same generators), held to
+    the reference's own tolerances — a bounded number of items per suite so that the CPU suite stays short."""
+    import ref_suites as rs
+    for sv_want, a in rs.diagonal_batches(60):
+        rs.check_diagonal(sv_want, a, *ref.svd_jac_2sided(a))
+    for zeros in (False, True):
+        for a in rs.random_examples(40, zeros):
+            rs.check_ndarray(a, *ref.svd_jac_2sided(a))
+        for a in rs.random_matrices(40, zeros, skip=250):
+            rs.check_matrix(a, *ref.svd_jac_2sided(a))
+    for a in rs.rank_deficient_examples(30):
+        rs.check_ndarray(a, *ref.svd_jac_2sided(a))
+    for a in rs.sparse_examples(40):
+        rs.check_ndarray(a, *ref.svd_jac_2sided(a))
+    for a in rs.sparse_matrices(30, skip=250):
+        rs.check_matrix(a, *ref.svd_jac_2sided(a))
+    for k, a in enumerate(rs.rank_deficient_matrices(1, 0)):
+        if k < 20:
+            rs.check_matrix(a, *ref.svd_jac_2sided(a))
