@@ -270,7 +270,9 @@ class DeviceCase:
             # per-matrix sweep counts of every launch are summed here: work per matrix is proportional to its sweeps
             self.sweep_sum = torch.zeros(1, dtype=torch.int64, device="cuda")
             self.launches = 0
-            if lib.nd4b_dev_svd_sweep_counter(dev, C.c_void_p(self.sweep_sum.data_ptr())):
+            self.pre_sum = torch.zeros(1, dtype=torch.int64, device="cuda")   # FP32 sweeps of the preconditioner
+            if lib.nd4b_dev_svd_sweep_counter(dev, C.c_void_p(self.sweep_sum.data_ptr())) or \
+                    lib.nd4b_dev_svd_pre_sweep_counter(dev, C.c_void_p(self.pre_sum.data_ptr())):
                 raise RuntimeError(lib.nd4b_last_error().decode())
             ws = lib.nd4b_dev_svd_workspace(units, 64, 64)
             self.work = torch.empty(max(ws, 8) // 8, **f64)
@@ -283,9 +285,15 @@ class DeviceCase:
             return None
         return float(self.sweep_sum.item()) / (self.launches * self.units)
 
+    def mean_pre_sweeps(self):
+        if self.sweeps is None or not self.launches:
+            return None
+        return float(self.pre_sum.item()) / (self.launches * self.units)
+
     def close(self):
         if self.sweeps is not None:
             self.lib.nd4b_dev_svd_sweep_counter(self.dev, None)
+            self.lib.nd4b_dev_svd_pre_sweep_counter(self.dev, None)
 
     def step(self, stream):
         L, p, d = self.lib, (lambda t: C.c_void_p(t.data_ptr())), self.dev
@@ -549,9 +557,12 @@ def run_ours(args):
     long_secs = max_over_ranks(time_device(torch, case, n_long, 0), device="cuda")
     sweeps = int(case.sweeps[0].item()) if case.sweeps is not None else None
     sweeps_mean = case.mean_sweeps()
+    pre_mean = case.mean_pre_sweeps() if case.sweeps is not None else None
     value = world * units * args.steps / secs
     launch_s = secs / args.steps
-    flop_unit = fpu * (sweeps_mean if sweeps_mean else 1)  # Jacobi work is proportional to the sweeps each matrix needed
+    # Jacobi work is proportional to the sweeps each matrix needed; with the single-precision preconditioner only the FP64
+    # sweeps and the four 64^3 FP64 products of the hand-over count as FP64 flop (the FP32 sweeps are reported beside them)
+    flop_unit = fpu * (sweeps_mean if sweeps_mean else 1) + (4 * 2 * 64 ** 3 if pre_mean else 0)
     achieved_gbs = bpu * units / launch_s / 1e9
     parity = {"device_resident": case.parity()} if rank == 0 else {}
     case.close()
@@ -564,7 +575,7 @@ def run_ours(args):
         if rank == 0:
             emit({"workload": args.workload, "ms_per_launch": 1e3 * launch_s, "ms_per_launch_sustained": 1e3 * long_secs / n_long,
                   "matrices_per_s": value, "gflops": value * flop_unit / 1e9, "hbm_gbs_algorithmic": achieved_gbs,
-                  "sweeps_max": sweeps, "sweeps_mean": sweeps_mean, "parity": parity})
+                  "sweeps_max": sweeps, "sweeps_mean": sweeps_mean, "fp32_pre_sweeps_mean": pre_mean, "parity": parity})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -635,7 +646,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if sweeps:
-            line["sweeps_max"], line["sweeps_mean"] = sweeps, sweeps_mean
+            line["sweeps_max"], line["sweeps_mean"], line["fp32_pre_sweeps_mean"] = sweeps, sweeps_mean, pre_mean
         if peaks:
             line["fp64_peaks_measured"] = peaks
 
@@ -650,12 +661,13 @@ def run_ours(args):
             s2 = time_device(torch, c2, n2, 3)
             s2 = max_over_ranks(s2, device="cuda")
             sw = c2.mean_sweeps() or 1
-            gf = world * u2 * n2 / s2 * f2 * sw / 1e9
+            pre2 = c2.mean_pre_sweeps() if name == "c5" else None
+            gf = world * u2 * n2 / s2 * (f2 * sw + (4 * 2 * 64 ** 3 if pre2 else 0)) / 1e9
             gbs = b2 * u2 * n2 / s2 / 1e9
             others[name] = {"workload": d2, "matrices_per_s": world * u2 * n2 / s2, "ms_per_launch": 1e3 * s2 / n2,
                             "gflops": gf, "hbm_gbs_algorithmic": gbs,
                             "frac_of_hbm_peak": gbs / hbm_peak, "frac_of_fp64_peak": gf / world / 1e3 / fp64_peak,
-                            "sweeps_mean": sw if name == "c5" else None,
+                            "sweeps_mean": sw if name == "c5" else None, "fp32_pre_sweeps_mean": pre2,
                             "sweeps_max": int(c2.sweeps[0].item()) if name == "c5" else None}
             if rank == 0:
                 others[name]["parity"] = c2.parity()

@@ -201,6 +201,9 @@ size_t nd4b_dev_svd_workspace(int64_t batch, int rows, int cols);
  * each matrix to *counter (device uint64, caller-initialised; NULL switches it off).  The Jacobi sweep count is data
  * dependent (C5: 10.06 on average, 12 at most), and work per matrix is proportional to it. */
 int nd4b_dev_svd_sweep_counter(int device, unsigned long long* counter);
+/* The same for the single-precision sweeps of the 64 x 64 preconditioner (csrc/svd_pre.cu), which runs when the dev / host
+ * call has its workspace (nd4b_dev_svd_workspace); ND4B_SVD_PRE=0 in the environment switches the preconditioner off. */
+int nd4b_dev_svd_pre_sweep_counter(int device, unsigned long long* counter);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 

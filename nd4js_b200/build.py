@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libnd4b.so")
-SOURCES = ["nd4b_api.cu", "matmul.cu", "cholesky.cu", "qr.cu", "qr_blocked.cu", "svd.cu", "svd_solve.cu", "solve.cu", "probes.cu"]
+SOURCES = ["nd4b_api.cu", "matmul.cu", "cholesky.cu", "qr.cu", "qr_blocked.cu", "svd.cu", "svd_pre.cu", "svd_solve.cu", "solve.cu", "probes.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--fmad=true",

@@ -69,8 +69,15 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
                             int64_t batch, int rows, int cols, int* sweeps, int* fail,
                             double* work, size_t work_bytes);
 
+// 64x64 preconditioner (svd_pre.cu): FP32 Jacobi, then V1 = orthogonalised rotation and G1 = A V1 into `work`
+// (svd64_pre_workspace_bytes(batch) bytes); *sweep_sum (may be null) accumulates the FP32 sweeps.
+size_t svd64_pre_workspace_bytes(int64_t batch);
+cudaError_t launch_svd64_pre(cudaStream_t s, const double* A, int64_t batch, double* work, unsigned long long* sweep_sum,
+                             const double** G1, const double** V1);
+
 // diagnostic: per-matrix sweep counts of the following SVD launches on `device` are added to *counter (device memory)
 void set_svd_sweep_counter(int device, unsigned long long* counter);
+void set_svd_pre_sweep_counter(int device, unsigned long long* counter);   // the same for the FP32 sweeps of the preconditioner
 
 // fp64 peak probes (tools/ and bench use them to measure the FP64 roofline denominators)
 cudaError_t launch_probe_dfma(cudaStream_t s, double* out, int iters, int blocks, int threads);

@@ -935,8 +935,9 @@ int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
   const int L = std::min(rows, cols);
   const size_t work_unit = nd4b::svd_workspace_bytes(1, rows, cols);
   auto launch = [&](const ChunkArgs& a) -> int {
+    const int n_kernels = (rows == 64 && cols == 64 && a.work_bytes) ? 3 : 1;   // preconditioner: FP32 Jacobi, V1 / G1, FP64 Jacobi
     return check_cuda_launch(nd4b::launch_svd_jac1(a.stream, a.in[0], a.out[0], a.out[1], a.out[2], a.count, rows, cols,
-                                                   a.dev->d_ints, a.dev->d_ints + 1, a.work, a.work_bytes), ctx);
+                                                   a.dev->d_ints, a.dev->d_ints + 1, a.work, a.work_bytes), ctx, n_kernels);
   };
   if (int rc = run_pipeline(ctx, batch, {{A, nullptr, (int64_t)rows * cols}},
                             {{nullptr, U, (int64_t)rows * L}, {nullptr, sv, (int64_t)L}, {nullptr, V, (int64_t)L * cols}},
@@ -1322,6 +1323,13 @@ int nd4b_dev_svd_sweep_counter(int device, unsigned long long* counter) {
   Context* ctx; int sms;
   if (int rc = dev_enter(device, &ctx, &sms)) return rc;
   nd4b::set_svd_sweep_counter(device, counter);
+  return ND4B_OK;
+}
+
+int nd4b_dev_svd_pre_sweep_counter(int device, unsigned long long* counter) {
+  Context* ctx; int sms;
+  if (int rc = dev_enter(device, &ctx, &sms)) return rc;
+  nd4b::set_svd_pre_sweep_counter(device, counter);
   return ND4B_OK;
 }
 

@@ -24,8 +24,27 @@
 
 namespace nd4b {
 
-constexpr int kMaxSweeps = 30;
+constexpr int kMaxSweeps = 60;
 constexpr double kEps = 2.220446049250313e-16;
+
+// Numerical-zero rule of the epilogues: a column whose norm is below 2^-200 of the largest one is a zero singular value
+// (its U vector comes from the orthonormal completion).  Together with the unit prescale below (largest entry in [1, 2)) and
+// the guard in the rotation test this keeps every product of the threshold test `d^2 > tol^2 |p|^2 |q|^2` in the normal
+// range: without it, columns that cancellation left at 1e-150 of the others (sparse rank-deficient input,
+// _generic_test_svd_decomp.js:257-274) were never orthogonalised against each other — d^2 underflows — and U = G / sigma
+// lost orthogonality.
+constexpr double kZeroRel = 0x1p-200;
+constexpr double kNormMin = 0x1p-400; // = kZeroRel^2: a column with |g|^2 below this (the largest entry is in [1, 2)) is numerically
+                                      // zero and is left alone — two parallel columns of a sparse matrix otherwise shed a rounding residue
+                                      // sixteen orders of magnitude smaller sweep after sweep without ever becoming orthogonal
+
+// Exact power of two that brings the largest entry into [1, 2) (QR / SVD are scale-equivariant and every operation of the
+// kernels commutes with a power-of-two scaling, so results do not change; zero, Inf and NaN give 1).
+__device__ __forceinline__ double pow2_prescale_unit(double amax) {
+  if (!(amax > 0.0) || !(amax < CUDART_INF)) return 1.0;
+  const int e = -ilogb(amax);
+  return scalbn(1.0, e > 1000 ? 1000 : e);
+}
 
 struct Rot { double c, s; };
 
@@ -173,7 +192,7 @@ __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* s
     }
     if (pad) rank = L + pads_before;
     perm[rank] = tid;
-    z = !(sj > smax * 1e-290) || !(sj >= DBL_MIN);
+    z = !(sj >= smax * kZeroRel) || !(sj >= DBL_MIN);
   }
   if (PADDED) __syncthreads();
   if (tid < N) {
@@ -279,7 +298,7 @@ svd64_smem_kernel(const double* __restrict__ A, double* __restrict__ U, double* 
         b += shfl_xor(b, o);
         d += shfl_xor(d, o);
       }
-      if (d * d > tol2 * a * b) {  // uniform inside the 8-lane group
+      if (d * d > tol2 * a * b && a > kNormMin && b > kNormMin) {  // uniform inside the 8-lane group
         rotated = 1;
         const Rot r = make_rotation(a, b, d);
 #pragma unroll
@@ -370,7 +389,8 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
   const double d = dhat * Dp * Dq;
   // The set-up runs warp-uniformly (if any pair of the warp rotates, every lane executes it and pairs below the threshold
   // discard the result with selects): a divergent branch here costs a reconvergence barrier in every step.
-  const bool rot = have && d * d > tol2 * na * nb;
+  // both squared norms above kNormMin = 2^-400, as one integer compare of the high words (they are never negative)
+  const bool rot = have && d * d > tol2 * na * nb && min(__double2hiint(na), __double2hiint(nb)) > 0x26f00000;
   if (__any_sync(kFull, rot)) {
     const double num = nb - na, den = 2.0 * d;
 #ifndef ND4B_SVD_T_FP64
@@ -524,10 +544,13 @@ __device__ __forceinline__ void cb_step(CbState& st, double2* wcs, int warp, int
 
 constexpr size_t kSvd64CbSmem = sizeof(double) * (2 * 64 * kSvd64LD + 64 + 2 * 4 * 136 + 4 * 16) + sizeof(int) * (64 * 3 + 4);
 
-template <int MINB, bool PADDED = false>
+// PRE: the iteration starts from (G1, V1) = (A V1, V1) with an orthogonal V1 prepared by svd_pre.cu instead of (A, I); A is
+// then the G1 array and V1 its accumulated rotation.
+template <int MINB, bool PADDED = false, bool PRE = false>
 __global__ void __launch_bounds__(128, MINB)
 svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V,
-               int64_t batch, int* sweeps_out, int* fail_out, unsigned long long* sweep_sum, int rows = 64, int cols = 64) {
+               int64_t batch, int* sweeps_out, int* fail_out, unsigned long long* sweep_sum, int rows = 64, int cols = 64,
+               const double* __restrict__ V1 = nullptr) {
   constexpr int N = 64, LD = kSvd64LD, XS = 136;       // XS: doubles per exchange record (4*32 column values + norm, D, 1/D)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Gs = reinterpret_cast<double*>(smem_raw);
@@ -570,10 +593,21 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
       st.g1[s] = (lane + 32 < cols && col < rows) ? ldg1_stream(a_in + col * cols + lane + 32) : 0.0;
     }
   }
+  if (PRE) {
+    const double* v_in = V1 + m * (N * N);
 #pragma unroll
-  for (int s = 0; s < 16; s++) {
-    st.v0[s] = (16 * warp + s == lane) ? 1.0 : 0.0;
-    st.v1[s] = (16 * warp + s == lane + 32) ? 1.0 : 0.0;
+    for (int s = 0; s < 16; s += 2) {
+      const double2 t0 = ldg2_stream(v_in + lane * N + 16 * warp + s);
+      const double2 t1 = ldg2_stream(v_in + (lane + 32) * N + 16 * warp + s);
+      st.v0[s] = t0.x; st.v0[s + 1] = t0.y;
+      st.v1[s] = t1.x; st.v1[s + 1] = t1.y;
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      st.v0[s] = (16 * warp + s == lane) ? 1.0 : 0.0;
+      st.v1[s] = (16 * warp + s == lane + 32) ? 1.0 : 0.0;
+    }
   }
   st.xg0 = st.xg1 = st.xv0 = st.xv1 = st.xn = 0.0;
   st.xd = st.xdi = 1.0;
@@ -586,7 +620,7 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
   if (lane == 0) sq[warp] = amax;
   __syncthreads();
   amax = fmax(fmax(sq[0], sq[1]), fmax(sq[2], sq[3]));
-  const double pre = pow2_prescale(amax);
+  const double pre = pow2_prescale_unit(amax);
   if (pre != 1.0) {
 #pragma unroll
     for (int s = 0; s < 16; s++) { st.g0[s] *= pre; st.g1[s] *= pre; }
@@ -716,7 +750,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
   __syncthreads();
   amax = 0.0;
   for (int w = 0; w < NW; w++) amax = fmax(amax, red_max[w]);
-  const double pre = pow2_prescale(amax), post = 1.0 / pre;   // scale guard, exact power of two
+  const double pre = pow2_prescale_unit(amax), post = 1.0 / pre;   // scale guard, exact power of two
   for (int64_t e = tid; e < (int64_t)rows * cols; e += T) {
     const double x = a_in[e] * pre;
     if (wide) Gt[e] = x;
@@ -751,7 +785,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
         for (int o = LPP / 2; o > 0; o >>= 1) {
           a += __shfl_xor_sync(gmask, a, o); b += __shfl_xor_sync(gmask, b, o); d += __shfl_xor_sync(gmask, d, o);
         }
-        if (d * d > tol2 * a * b) {
+        if (d * d > tol2 * a * b && a > kNormMin && b > kNormMin) {
           rotated = 1;
           const Rot r = make_rotation(a, b, d);
           for (int i = sub; i < mm; i += LPP) {
@@ -797,7 +831,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
       smax = fmax(smax, sk);
     }
     perm[rank] = j;
-    zero_flag[j] = !(sj > smax * 1e-290) || !(sj >= DBL_MIN);
+    zero_flag[j] = !(sj >= smax * kZeroRel) || !(sj >= DBL_MIN);
     done_flag[j] = 0;
   }
   __syncthreads();
@@ -875,7 +909,7 @@ svd_tiny_kernel(const double* __restrict__ A, double* __restrict__ U, double* __
     double* permd = sig + 8;
     double amax = 0.0;
     for (int e = 0; e < na; e++) amax = fmax(amax, fabs(G[e]));
-    const double pre = pow2_prescale(amax);
+    const double pre = pow2_prescale_unit(amax);
     if (pre != 1.0)
       for (int e = 0; e < na; e++) G[e] *= pre;
     for (int e = 0; e < n * n; e++) Vv[e] = 0.0;
@@ -892,7 +926,7 @@ svd_tiny_kernel(const double* __restrict__ A, double* __restrict__ U, double* __
             const double x = G[i * n + p], y = G[i * n + q];
             a = fma(x, x, a); b = fma(y, y, b); d = fma(x, y, d);
           }
-          if (!(d * d > tol2 * a * b)) continue;
+          if (!(d * d > tol2 * a * b && a > kNormMin && b > kNormMin)) continue;
           converged = false;
           const double zeta = (b - a) / (2.0 * d);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
@@ -923,7 +957,7 @@ svd_tiny_kernel(const double* __restrict__ A, double* __restrict__ U, double* __
       int rank = 0;
       for (int k = 0; k < n; k++) rank += (sig[k] > sig[j]) || (sig[k] == sig[j] && k < j);
       permd[rank] = (double)j;
-      if (!(sig[j] > smax * 1e-290) || !(sig[j] >= DBL_MIN)) zero_mask |= 1u << j;
+      if (!(sig[j] >= smax * kZeroRel) || !(sig[j] >= DBL_MIN)) zero_mask |= 1u << j;
     }
     for (int j = 0; j < n; j++)
       if (!((zero_mask >> j) & 1)) {
@@ -999,13 +1033,27 @@ svd_tiny_kernel(const double* __restrict__ A, double* __restrict__ U, double* __
 
 // Diagnostic: device counter that every following SVD launch on `device` adds its per-matrix sweep counts to (nullptr: off).
 static unsigned long long* g_sweep_sum[64] = {nullptr};
+static unsigned long long* g_pre_sweep_sum[64] = {nullptr};
 void set_svd_sweep_counter(int device, unsigned long long* counter) {
   if (device >= 0 && device < 64) g_sweep_sum[device] = counter;
+}
+void set_svd_pre_sweep_counter(int device, unsigned long long* counter) {
+  if (device >= 0 && device < 64) g_pre_sweep_sum[device] = counter;
 }
 
 constexpr size_t kSvdGenSmemLimit = 200 * 1024;
 
+static bool svd_pre_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* ev = getenv("ND4B_SVD_PRE");
+    on = ev ? atoi(ev) : 1;   // 0: the plain FP64 iteration from (A, I), for A/B timing
+  }
+  return on != 0;
+}
+
 size_t svd_workspace_bytes(int64_t batch, int rows, int cols) {
+  if (rows == 64 && cols == 64 && svd_pre_enabled()) return svd64_pre_workspace_bytes(batch);   // V0, G1, V1 of the preconditioner
   if (rows <= 64 && cols <= 64) return 0;   // register kernel (padded) or scratch in shared memory
   if (sizeof(double) * svd_gen_scratch_doubles(rows, cols) <= kSvdGenSmemLimit) return 0;  // scratch in shared memory
   return sizeof(double) * (size_t)batch * svd_gen_scratch_doubles(rows, cols);
@@ -1066,7 +1114,19 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
       variant = ev ? atoi(ev) : 0;  // 1 = the shared-memory baseline kernel (kept for A/B profiling)
     }
     if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail, ssum);
-    else svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail, ssum);
+    else if (svd_pre_enabled() && work != nullptr && work_bytes >= svd64_pre_workspace_bytes(batch)) {
+      // FP32 Jacobi -> orthogonalised V1, G1 = A V1 -> FP64 Jacobi from (G1, V1): svd_pre.cu
+      static bool pre_attr_set[64] = {false};
+      if (dev >= 0 && dev < 64 && !pre_attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(svd64cb_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSvd64CbSmem);
+        if (e != cudaSuccess) return e;
+        pre_attr_set[dev] = true;
+      }
+      const double *g1 = nullptr, *v1 = nullptr;
+      cudaError_t e = launch_svd64_pre(s, A, batch, work, (dev >= 0 && dev < 64) ? g_pre_sweep_sum[dev] : nullptr, &g1, &v1);
+      if (e != cudaSuccess) return e;
+      svd64cb_kernel<2, false, true><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(g1, U, sv, V, batch, sweeps, fail, ssum, 64, 64, v1);
+    } else svd64cb_kernel<2><<<(unsigned)batch, 128, kSvd64CbSmem, s>>>(A, U, sv, V, batch, sweeps, fail, ssum);
     return cudaGetLastError();
   }
   const size_t per_matrix = sizeof(double) * svd_gen_scratch_doubles(rows, cols);

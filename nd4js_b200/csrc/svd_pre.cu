@@ -1,0 +1,454 @@
+// svd_pre.cu — single-precision preconditioner of the 64x64 one-sided Jacobi SVD (BASELINE config C5).
+//
+// A Jacobi sweep costs the same whether it rotates by 40 degrees or by 1e-9, and of the ~10 sweeps the FP64 kernel
+// (svd.cu, svd64cb_kernel) needs on a random 64x64 matrix all but the last two only bring the off-diagonal cosines from
+// O(1) down to ~1e-6 — work that does not need 53 bits.  So the sweeps are split:
+//
+//   1. svd64_pre32_kernel : the same one-sided Jacobi (odd-even ordering with exchange, square-root-free scaled rotations,
+//                           warp-owned columns in registers) on an FP32 copy of A, with packed FP32x2 arithmetic (FFMA2 /
+//                           FMUL2: the two rows a lane owns of a column are one 64-bit register pair), until a sweep sees no
+//                           cosine above 1e-2 (quadratic convergence then leaves ~1e-6): ~8 cheap sweeps.  Only the
+//                           accumulated rotation V0 (FP32, orthogonal to ~1e-5) leaves the kernel.
+//   2. svd64_ortho_kernel : FP64, DMMA from shared memory: V1 = V0 (I + E)^(-1/2) with E = V0^T V0 - I, as the polynomial
+//                           I - E/2 + 3 E^2 / 8 (- 5 E^3 / 16 when |E|_F says it matters) — orthogonal to working precision —
+//                           and G1 = A V1, whose columns are orthogonal to ~1e-6.
+//   3. svd64cb_kernel<.., PRE> (svd.cu): the FP64 Jacobi started from (G1, V1) instead of (A, I): two rotating sweeps and
+//                           the confirming one, the same convergence test and epilogue as before, so the results obey the
+//                           same bounds.  Any orthogonal V1 is a valid start: if step 1 or 2 goes wrong (NaN input, |E| not
+//                           small) step 2 hands over (A, I) and step 3 is the plain algorithm.
+//
+// Contract, ordering and sign rules: see svd.cu (nd4js src/la/svd_jac_2sided.js:30-144, _svd_jac_utils.js:123-188).
+#include "common.cuh"
+#include "kernels.h"
+#include <float.h>
+
+namespace nd4b {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float hsum2(u64 x) { float lo, hi; unpack2(x, lo, hi); return lo + hi; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int N>
+__device__ __forceinline__ void halvef(float (&v)[N], bool bit, int mask) {
+#pragma unroll
+  for (int k = 0; k < N / 2; k++) {
+    const float send = bit ? v[k] : v[k + N / 2];
+    const float keep = bit ? v[k + N / 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(kFull, send, mask);
+  }
+}
+
+// every lane of 4-lane group grp ends up with the warp total of element grp
+__device__ __forceinline__ float reduce8f(float (&pd)[8], int lane) {
+  halvef<8>(pd, (lane & 16) != 0, 16);
+  float h4[4] = {pd[0], pd[1], pd[2], pd[3]};
+  halvef<4>(h4, (lane & 8) != 0, 8);
+  float h2[2] = {h4[0], h4[1]};
+  halvef<2>(h2, (lane & 4) != 0, 4);
+  float d = h2[0];
+  d += __shfl_xor_sync(kFull, d, 2);
+  d += __shfl_xor_sync(kFull, d, 1);
+  return d;
+}
+
+// State of one lane: rows l and l+32 (packed) of G-hat and V-hat for the warp's 16 column slots; the scaled-rotation
+// bookkeeping is that of CbState in svd.cu, in single precision.
+struct P32State {
+  u64 g[16], v[16];
+  u64 xg, xv;                       // the borrowed boundary column in B steps
+  float e, o;                       // cached true |g|^2 of slots 2*grp, 2*grp+1
+  float de, dei, dq, dqi;           // D and 1/D of the even / odd slot
+  float xn, xd, xdi;
+};
+
+constexpr float kPreTol2 = 1.4551915e-11f;   // (64 * 2^-24)^2: rotate while cos^2 is above the FP32 noise
+constexpr float kPreBig2 = 1e-4f;            // a sweep that saw no cos^2 above this is the last one (then ~1e-6 remains)
+constexpr int kPreMaxSweeps = 12;
+
+struct P32Rot { float alpha, beta; };
+
+__device__ __forceinline__ P32Rot p32_params(float dhat, float na, float nb, float Dp, float Dpi, float Dq, float Dqi, bool have,
+                                             float& na2, float& nb2, float& Dp2, float& Dpi2, float& Dq2, float& Dqi2, int& big) {
+  P32Rot r;
+  r.alpha = 0.f; r.beta = 0.f;
+  na2 = na; nb2 = nb; Dp2 = Dp; Dpi2 = Dpi; Dq2 = Dq; Dqi2 = Dqi;
+  const float d = dhat * Dp * Dq;
+  const float ab = na * nb;
+  const bool rot = have && d * d > kPreTol2 * ab && ab > 1e-25f;
+  if (have && d * d > kPreBig2 * ab) big = 1;
+  if (__any_sync(kFull, rot)) {   // warp-uniform set-up, as in cb_params
+    const float num = nb - na, den = 2.f * d;
+    const float im = rcp_approx(fmaxf(fabsf(num), fabsf(den)));
+    const float n1 = fabsf(num) * im, d1 = fabsf(den) * im;      // the larger one is 1
+    const float S = fmaf(n1, n1, d1 * d1);                       // in [1, 2]
+    const float y = rsqrt_approx(S);
+    float t = d1 * rcp_approx(fmaf(S, y, n1));                   // |den| / (|num| + sqrt(num^2 + den^2))
+    t = __int_as_float(__float_as_int(t) | ((__float_as_int(num) ^ __float_as_int(den)) & 0x80000000));
+    const float w = fmaf(t, t, 1.f);
+    float c = rsqrt_approx(w);
+    c = c * fmaf(-0.5f * w * c, c, 1.5f);                        // one Newton step: V0 stays orthogonal to ~1e-5 over a run
+    const float rc = w * c;
+    const float na_r = fmaxf(fmaf(-t, d, na), 0.f), nb_r = fmaxf(fmaf(t, d, nb), 0.f);
+    r.alpha = rot ? t * Dq * Dpi : 0.f;
+    r.beta = rot ? t * Dp * Dqi : 0.f;
+    Dp2 = rot ? c * Dp : Dp; Dq2 = rot ? c * Dq : Dq; Dpi2 = rot ? rc * Dpi : Dpi; Dqi2 = rot ? rc * Dqi : Dqi;
+    na2 = rot ? na_r : na;
+    nb2 = rot ? nb_r : nb;
+  }
+  return r;
+}
+
+// (p, q) -> (p - alpha q, q + beta p) on both rows at once, stored exchanged
+__device__ __forceinline__ void rot_swap2(u64& xa, u64& xb, u64 nalpha2, u64 beta2) {
+  const u64 np = fma2(nalpha2, xb, xa);
+  const u64 nq = fma2(beta2, xa, xb);
+  xa = nq;
+  xb = np;
+}
+
+template <bool STEP_B>
+__device__ __forceinline__ void p32_step(P32State& st, float4* wcs, int warp, int lane, int& big) {
+  const int grp = lane >> 2;
+  float pd[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (!STEP_B) pd[j] = hsum2(mul2(st.g[2 * j], st.g[2 * j + 1]));
+    else if (j < 7) pd[j] = hsum2(mul2(st.g[2 * j + 1], st.g[2 * j + 2]));
+    else pd[j] = hsum2(mul2(st.g[15], st.xg));
+  }
+  const float dhat = reduce8f(pd, lane);
+  float na, nb, Dp, Dpi, Dq, Dqi;
+  bool have = true;
+  if (!STEP_B) { na = st.e; nb = st.o; Dp = st.de; Dpi = st.dei; Dq = st.dq; Dqi = st.dqi; }
+  else {
+    const float e_next = __shfl_down_sync(kFull, st.e, 4);
+    const float de_next = __shfl_down_sync(kFull, st.de, 4);
+    const float dei_next = __shfl_down_sync(kFull, st.dei, 4);
+    na = st.o; Dp = st.dq; Dpi = st.dqi;
+    nb = (grp < 7) ? e_next : st.xn;
+    Dq = (grp < 7) ? de_next : st.xd;
+    Dqi = (grp < 7) ? dei_next : st.xdi;
+    have = (grp < 7) || (warp < 3);
+  }
+  float na2, nb2, Dp2, Dpi2, Dq2, Dqi2;
+  const P32Rot r = p32_params(dhat, na, nb, Dp, Dpi, Dq, Dqi, have, na2, nb2, Dp2, Dpi2, Dq2, Dqi2, big);
+  if (!STEP_B) {
+    st.e = nb2; st.de = Dq2; st.dei = Dqi2;
+    st.o = na2; st.dq = Dp2; st.dqi = Dpi2;
+  } else {
+    const float n_prev = __shfl_up_sync(kFull, na2, 4);
+    const float d_prev = __shfl_up_sync(kFull, Dp2, 4);
+    const float di_prev = __shfl_up_sync(kFull, Dpi2, 4);
+    if (have) { st.o = nb2; st.dq = Dq2; st.dqi = Dqi2; }
+    if (grp > 0) { st.e = n_prev; st.de = d_prev; st.dei = di_prev; }
+    if (grp == 7 && have) { st.xn = na2; st.xd = Dp2; st.xdi = Dpi2; }
+  }
+  // (-alpha, -alpha, beta, beta) of the 8 pairs to every lane through a warp-private line: one LDS.128 per pair delivers
+  // both packed multipliers
+  __syncwarp();
+  if ((lane & 3) == 0) wcs[grp] = make_float4(-r.alpha, -r.alpha, r.beta, r.beta);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float4 ab = wcs[j];
+    const u64 na2p = pack2(ab.x, ab.y), b2p = pack2(ab.z, ab.w);
+    if (!STEP_B) {
+      rot_swap2(st.g[2 * j], st.g[2 * j + 1], na2p, b2p);
+      rot_swap2(st.v[2 * j], st.v[2 * j + 1], na2p, b2p);
+    } else if (j < 7) {
+      rot_swap2(st.g[2 * j + 1], st.g[2 * j + 2], na2p, b2p);
+      rot_swap2(st.v[2 * j + 1], st.v[2 * j + 2], na2p, b2p);
+    } else if (warp < 3) {
+      rot_swap2(st.g[15], st.xg, na2p, b2p);
+      rot_swap2(st.v[15], st.xv, na2p, b2p);
+    }
+  }
+}
+
+constexpr int kPreXS = 68;   // u64 per exchange record: 32 g + 32 v + (norm, D, 1/D) + pad
+
+// One CTA (4 warps) per matrix.  V0 (FP32, row-major [component][column slot]) is the only result.
+__global__ void __launch_bounds__(128, 4)
+svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t batch, unsigned long long* sweep_sum) {
+  __shared__ __align__(16) u64 xch[2 * 4 * kPreXS];
+  __shared__ __align__(16) float4 wcs_all[4 * 8];
+  __shared__ double red[4];
+  const int64_t m = blockIdx.x;
+  if (m >= batch) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2;
+  const double* a_in = A + m * 4096;
+  float4* wcs = wcs_all + 8 * warp;
+  float* wsc = reinterpret_cast<float*>(wcs);   // the same 128 bytes hold the 16 slot scales between sweeps
+
+  P32State st;
+  {
+    double t0[16], t1[16];
+    double amax = 0.0;
+#pragma unroll
+    for (int s = 0; s < 16; s += 2) {
+      const double2 x0 = ldg2(a_in + lane * 64 + 16 * warp + s);          // read again by the FP64 kernels: keep it in L2
+      const double2 x1 = ldg2(a_in + (lane + 32) * 64 + 16 * warp + s);
+      t0[s] = x0.x; t0[s + 1] = x0.y; t1[s] = x1.x; t1[s + 1] = x1.y;
+      amax = fmax(amax, fmax(fmax(fabs(x0.x), fabs(x0.y)), fmax(fabs(x1.x), fabs(x1.y))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, shfl_xor(amax, o));
+    if (lane == 0) red[warp] = amax;
+    __syncthreads();
+    amax = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+    // exact power of two that brings the largest entry into [1, 2): the FP32 copy then neither overflows nor loses the
+    // matrix to underflow (entries below 2^-126 of the largest become zero, which only costs FP64 sweeps later)
+    double pre = 1.0;
+    if (amax > 0.0 && amax < CUDART_INF) { const int e = -ilogb(amax); pre = scalbn(1.0, e > 1000 ? 1000 : e); }
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      st.g[s] = pack2((float)(t0[s] * pre), (float)(t1[s] * pre));
+      st.v[s] = pack2((16 * warp + s == lane) ? 1.f : 0.f, (16 * warp + s == lane + 32) ? 1.f : 0.f);
+    }
+  }
+  st.xg = st.xv = 0ull;
+  st.xn = 0.f; st.xd = st.xdi = 1.f;
+
+  int sweeps = 0;
+  bool more = true;
+  while (sweeps < kPreMaxSweeps && more) {
+    sweeps++;
+    int big = 0;
+    st.de = st.dei = st.dq = st.dqi = 1.f;
+    {  // exact slot norms: 16 values -> 2 per 4-lane group
+      float n2[16];
+#pragma unroll
+      for (int s = 0; s < 16; s++) n2[s] = hsum2(mul2(st.g[s], st.g[s]));
+      halvef<16>(n2, (lane & 16) != 0, 16);
+      float h8[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) h8[k] = n2[k];
+      halvef<8>(h8, (lane & 8) != 0, 8);
+      float h4[4] = {h8[0], h8[1], h8[2], h8[3]};
+      halvef<4>(h4, (lane & 4) != 0, 4);
+      float e = h4[0], o = h4[1];
+      e += __shfl_xor_sync(kFull, e, 2); o += __shfl_xor_sync(kFull, o, 2);
+      e += __shfl_xor_sync(kFull, e, 1); o += __shfl_xor_sync(kFull, o, 1);
+      st.e = e; st.o = o;
+    }
+#pragma unroll 1
+    for (int sp2 = 0; sp2 < 32; sp2++) {
+      p32_step<false>(st, wcs, warp, lane, big);
+      u64* out = xch + warp * kPreXS;   // hand my first column to the left neighbour for the B step
+      if (warp > 0) {
+        out[lane] = st.g[0]; out[32 + lane] = st.v[0];
+        if (lane == 0) { float* sc = reinterpret_cast<float*>(out + 64); sc[0] = st.e; sc[1] = st.de; sc[2] = st.dei; }
+      }
+      __syncthreads();
+      if (warp < 3) {
+        const u64* in = xch + (warp + 1) * kPreXS;
+        st.xg = in[lane]; st.xv = in[32 + lane];
+        const float* sc = reinterpret_cast<const float*>(in + 64);
+        st.xn = sc[0]; st.xd = sc[1]; st.xdi = sc[2];
+      }
+      p32_step<true>(st, wcs, warp, lane, big);
+      u64* out2 = xch + 4 * kPreXS + (warp + 1) * kPreXS;   // give the borrowed (rotated) column back
+      if (warp < 3) {
+        out2[lane] = st.xg; out2[32 + lane] = st.xv;
+        if (lane == 28) { float* sc = reinterpret_cast<float*>(out2 + 64); sc[0] = st.xn; sc[1] = st.xd; sc[2] = st.xdi; }
+      }
+      __syncthreads();
+      if (warp > 0) {
+        const u64* in2 = xch + 4 * kPreXS + warp * kPreXS;
+        st.g[0] = in2[lane]; st.v[0] = in2[32 + lane];
+        if (grp == 0) { const float* sc = reinterpret_cast<const float*>(in2 + 64); st.e = sc[0]; st.de = sc[1]; st.dei = sc[2]; }
+      }
+    }
+    // fold the scales back into the columns
+    __syncwarp();
+    if ((lane & 3) == 0) { wsc[2 * grp] = st.de; wsc[2 * grp + 1] = st.dq; }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const float D = wsc[s];
+      const u64 D2 = pack2(D, D);
+      st.g[s] = mul2(st.g[s], D2);
+      st.v[s] = mul2(st.v[s], D2);
+    }
+    __syncwarp();
+    more = __syncthreads_or(big) != 0;
+  }
+  if (tid == 0 && sweep_sum) atomicAdd(sweep_sum, (unsigned long long)sweeps);
+
+  float* v_out = V0 + m * 4096;
+#pragma unroll
+  for (int s = 0; s < 16; s += 4) {
+    float lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) unpack2(st.v[s + k], lo[k], hi[k]);
+    *reinterpret_cast<float4*>(v_out + lane * 64 + 16 * warp + s) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4*>(v_out + (lane + 32) * 64 + 16 * warp + s) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// V1 = V0 (I + E)^(-1/2),  G1 = A V1  — FP64 on the DMMA pipe, operands in shared memory.
+// 8 warps per matrix; warp w owns the 8 output rows 8w..8w+7 (eight 8x8 tiles), lane = 4g + t holds C[g][2t], C[g][2t+1]
+// of every tile.  Row strides: 72 doubles for matrices read as the B operand (element [k0+t][n0+g]: conflict-free when the
+// stride is 8 mod 16), 68 for A = the A operand of the last product (element [i0+g][k0+t]: 4 mod 16).  E is symmetric, so
+// wherever E is the A operand it is read through its transpose with the conflict-free pattern.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOrthoLD = 72, kOrthoLDA = 68;
+constexpr size_t kOrthoSmem = sizeof(double) * (3 * 64 * kOrthoLD + 16);
+
+template <class FA, class FB>
+__device__ __forceinline__ void tile_row_product(double (&acc)[8][2], FA fa, FB fb) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < 64; k0 += 4) {
+    const double a = fa(k0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) dmma884(acc[j][0], acc[j][1], a, fb(k0, j));
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+svd64_ortho_kernel(const double* __restrict__ A, const float* __restrict__ V0, double* __restrict__ G1, double* __restrict__ V1,
+                   int64_t batch) {
+  extern __shared__ __align__(16) double osm[];
+  double* Bv = osm;                         // V0 (stride 72), later A (stride 68)
+  double* Be = Bv + 64 * kOrthoLD;          // E, later V1
+  double* Bp = Be + 64 * kOrthoLD;          // E^2, then P
+  double* red = Bp + 64 * kOrthoLD;         // [8] partial |E|_F^2
+  const int64_t m = blockIdx.x;
+  if (m >= batch) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int i0 = 8 * warp;
+  const double* a_in = A + m * 4096;
+  const float* v_in = V0 + m * 4096;
+  double* g_out = G1 + m * 4096;
+  double* v_out = V1 + m * 4096;
+
+  // A in registers until V0's buffer is free (row r = idx / 32, 16-byte column pair c2 = idx % 32)
+  double2 areg[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) areg[r] = ldg2_stream(a_in + 2 * (tid + 256 * r));
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int idx = tid + 256 * r, row = idx >> 4, c4 = (idx & 15) * 4;
+    const float4 x = __ldcs(reinterpret_cast<const float4*>(v_in) + idx);
+    double* d = Bv + row * kOrthoLD + c4;
+    *reinterpret_cast<double2*>(d) = make_double2((double)x.x, (double)x.y);
+    *reinterpret_cast<double2*>(d + 2) = make_double2((double)x.z, (double)x.w);
+  }
+  __syncthreads();
+
+  double acc[8][2];
+  // E = V0^T V0 - I
+  tile_row_product(acc, [&](int k0) { return Bv[(k0 + t) * kOrthoLD + i0 + g]; },
+                   [&](int k0, int j) { return Bv[(k0 + t) * kOrthoLD + 8 * j + g]; });
+  double ne = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int col = 8 * j + 2 * t;
+    const double e0 = acc[j][0] - ((i0 + g == col) ? 1.0 : 0.0), e1 = acc[j][1] - ((i0 + g == col + 1) ? 1.0 : 0.0);
+    ne = fma(e0, e0, fma(e1, e1, ne));
+    *reinterpret_cast<double2*>(Be + (i0 + g) * kOrthoLD + col) = make_double2(e0, e1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ne += shfl_xor(ne, o);
+  if (lane == 0) red[warp] = ne;
+  __syncthreads();
+  ne = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) ne += red[w];
+
+  if (!(ne <= 1e-4)) {
+    // V0 is not close to orthogonal (NaN / Inf input, or the FP32 run went wrong): hand over the plain start (A, I)
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int idx = tid + 256 * r, row = idx >> 5, c2 = (idx & 31) * 2;
+      *reinterpret_cast<double2*>(g_out + 2 * idx) = areg[r];
+      *reinterpret_cast<double2*>(v_out + 2 * idx) = make_double2(row == c2 ? 1.0 : 0.0, row == c2 + 1 ? 1.0 : 0.0);
+    }
+    return;
+  }
+
+  // F = E E (E read through its transpose as the A operand)
+  tile_row_product(acc, [&](int k0) { return Be[(k0 + t) * kOrthoLD + i0 + g]; },
+                   [&](int k0, int j) { return Be[(k0 + t) * kOrthoLD + 8 * j + g]; });
+  // The neglected term of (I + E)^(-1/2) leaves 5/8 |E^3| in V1^T V1 - I: below ~1e-15 it is noise
+  const bool cubic = ne * sqrt(ne) > 2e-15;   // CTA-uniform
+  if (cubic) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      *reinterpret_cast<double2*>(Bp + (i0 + g) * kOrthoLD + 8 * j + 2 * t) = make_double2(acc[j][0], acc[j][1]);
+    __syncthreads();
+    double f3[8][2];
+    tile_row_product(f3, [&](int k0) { return Be[(k0 + t) * kOrthoLD + i0 + g]; },
+                     [&](int k0, int j) { return Bp[(k0 + t) * kOrthoLD + 8 * j + g]; });
+    __syncthreads();   // every warp has read F before P overwrites it
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc[j][0] = fma(-5.0 / 6.0, f3[j][0], acc[j][0]); acc[j][1] = fma(-5.0 / 6.0, f3[j][1], acc[j][1]); }   // 3/8 (F - 5/6 E^3)
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int col = 8 * j + 2 * t;
+    const double2 e = *reinterpret_cast<const double2*>(Be + (i0 + g) * kOrthoLD + col);
+    const double p0 = fma(0.375, acc[j][0], fma(-0.5, e.x, (i0 + g == col) ? 1.0 : 0.0));
+    const double p1 = fma(0.375, acc[j][1], fma(-0.5, e.y, (i0 + g == col + 1) ? 1.0 : 0.0));
+    *reinterpret_cast<double2*>(Bp + (i0 + g) * kOrthoLD + col) = make_double2(p0, p1);
+  }
+  __syncthreads();
+
+  // V1 = V0 P  -> global and Be
+  tile_row_product(acc, [&](int k0) { return Bv[(i0 + g) * kOrthoLD + k0 + t]; },
+                   [&](int k0, int j) { return Bp[(k0 + t) * kOrthoLD + 8 * j + g]; });
+  __syncthreads();   // all reads of V0 (Bv) and of E (Be) are done
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int col = 8 * j + 2 * t;
+    *reinterpret_cast<double2*>(Be + (i0 + g) * kOrthoLD + col) = make_double2(acc[j][0], acc[j][1]);
+    *reinterpret_cast<double2*>(v_out + (i0 + g) * 64 + col) = make_double2(acc[j][0], acc[j][1]);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int idx = tid + 256 * r, row = idx >> 5, c2 = (idx & 31) * 2;
+    *reinterpret_cast<double2*>(Bv + row * kOrthoLDA + c2) = areg[r];
+  }
+  __syncthreads();
+
+  // G1 = A V1
+  tile_row_product(acc, [&](int k0) { return Bv[(i0 + g) * kOrthoLDA + k0 + t]; },
+                   [&](int k0, int j) { return Be[(k0 + t) * kOrthoLD + 8 * j + g]; });
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    *reinterpret_cast<double2*>(g_out + (i0 + g) * 64 + 8 * j + 2 * t) = make_double2(acc[j][0], acc[j][1]);
+}
+
+// workspace per matrix: V0 (4096 floats), G1, V1 (4096 doubles each)
+size_t svd64_pre_workspace_bytes(int64_t batch) { return (size_t)batch * (4096 * 4 + 2 * 4096 * 8); }
+
+cudaError_t launch_svd64_pre(cudaStream_t s, const double* A, int64_t batch, double* work, unsigned long long* sweep_sum,
+                             const double** G1, const double** V1) {
+  float* v0 = reinterpret_cast<float*>(work);
+  double* g1 = work + (size_t)batch * 2048;
+  double* v1 = g1 + (size_t)batch * 4096;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(svd64_ortho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrthoSmem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  svd64_pre32_kernel<<<(unsigned)batch, 128, 0, s>>>(A, v0, batch, sweep_sum);
+  svd64_ortho_kernel<<<(unsigned)batch, 256, kOrthoSmem, s>>>(A, v0, g1, v1, batch);
+  *G1 = g1;
+  *V1 = v1;
+  return cudaGetLastError();
+}
+
+}  // namespace nd4b
