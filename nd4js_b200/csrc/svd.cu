@@ -409,8 +409,12 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(Sf));
     float rf;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(fmaf(Sf, yf, an)));   // 1 / (|num| + sqrt(S)), denominator >= 1
-    const float tf = __int_as_float(__float_as_int(ad * rf) | ((__float_as_int(nf) ^ __float_as_int(df)) & 0x80000000));
-    const double t = (double)tf;
+    // t = den / (|num| + sqrt(S)) with the quotient's single-precision reciprocal applied to the DOUBLE numerator: when
+    // |den| is more than 2^126 times smaller than |num| (a rounding residue that is still parallel to a large column:
+    // sparse rank-deficient input) the single-precision numerator would flush to zero, the rotation would be the
+    // identity, and the pair would be "rotated" in every sweep for ever
+    const float rfs = __int_as_float(__float_as_int(rf) | (__float_as_int(nf) & 0x80000000));
+    const double t = (den * scale) * (double)rfs;
     // c = 1/sqrt(1 + t^2) and 1/c = sqrt(1 + t^2) in full precision from the t actually used (off the critical path)
     const double w = fma(t, t, 1.0);                                     // in [1, 2]
     double c;

@@ -4,8 +4,8 @@
 // (svd.cu, svd64cb_kernel) needs on a random 64x64 matrix all but the last two only bring the off-diagonal cosines from
 // O(1) down to ~1e-6 — work that does not need 53 bits.  So the sweeps are split:
 //
-//   1. svd64_pre32_kernel : the same one-sided Jacobi (odd-even ordering with exchange, square-root-free scaled rotations,
-//                           warp-owned columns in registers) on an FP32 copy of A, with packed FP32x2 arithmetic (FFMA2 /
+//   1. svd64_pre32_kernel : one-sided Jacobi (block round-robin ordering with fixed register slots, square-root-free scaled
+//                           rotations, warp-owned columns in registers) on an FP32 copy of A, with packed FP32x2 arithmetic (FFMA2 /
 //                           FMUL2: the two rows a lane owns of a column are one 64-bit register pair), until a sweep sees no
 //                           cosine above 1e-2 (quadratic convergence then leaves ~1e-6): ~8 cheap sweeps.  Only the
 //                           accumulated rotation V0 (FP32, orthogonal to ~1e-5) leaves the kernel.
@@ -57,33 +57,35 @@ __device__ __forceinline__ float reduce8f(float (&pd)[8], int lane) {
   return d;
 }
 
-// State of one lane: rows l and l+32 (packed) of G-hat and V-hat for the warp's 16 column slots; the scaled-rotation
-// bookkeeping is that of CbState in svd.cu, in single precision.
-struct P32State {
-  u64 g[16], v[16];
-  u64 xg, xv;                       // the borrowed boundary column in B steps
-  float e, o;                       // cached true |g|^2 of slots 2*grp, 2*grp+1
-  float de, dei, dq, dqi;           // D and 1/D of the even / odd slot
-  float xn, xd, xdi;
-};
+// Ordering.  The 64 columns are eight blocks of eight; a warp holds two blocks, A and B, in FIXED registers (slot i of a
+// block never moves inside a round), lane l owning rows l and l+32 (one packed register pair) of every slot of G-hat and
+// V-hat.  A sweep is seven rounds of a round-robin tournament between the blocks (warp w plays positions w and 7-w;
+// after each round the blocks move one position on through shared memory, two barriers per round), and a round is the
+// eight "cross" steps  { (A_i, B_(i+s) mod 8) : i = 0..7 },  s = 0..7, which meet every pair of the two blocks once; the
+// 2 x 28 pairs inside the blocks are met in the first round by seven steps  { (X_i, X_(i xor m)) },  m = 1..7.  63 steps
+// of 32 disjoint pairs = all 2016 pairs, like the odd-even ordering it replaces, but no column ever changes its
+// register inside a round: the step bodies are unrolled with compile-time slot indices (the exchange of the odd-even
+// ordering cost a register move per element and step, two barriers and a boundary column through shared memory per step).
+//
+// Scaled ("fast") rotations as in svd.cu: column = D * g-hat, a rotation is  p -= alpha q;  q += beta p  (one packed FMA
+// each), D folded back at the end of every round.  The 4-lane group g keeps the cached true |.|^2, D and 1/D of A-slot g
+// and of the B-slot it currently plays against (ownership of the B side moves one group on per cross step: 3 shuffles).
+struct P32Col { float n, d, di; };   // cached |g|^2, scale D, 1/D of one column
 
 constexpr float kPreTol2 = 1.4551915e-11f;   // (64 * 2^-24)^2: rotate while cos^2 is above the FP32 noise
 constexpr float kPreBig2 = 1e-4f;            // a sweep that saw no cos^2 above this is the last one (then ~1e-6 remains)
 constexpr int kPreMaxSweeps = 12;
 
-struct P32Rot { float alpha, beta; };
-
-__device__ __forceinline__ P32Rot p32_params(float dhat, float na, float nb, float Dp, float Dpi, float Dq, float Dqi, bool have,
-                                             float& na2, float& nb2, float& Dp2, float& Dpi2, float& Dq2, float& Dqi2, int& big) {
-  P32Rot r;
-  r.alpha = 0.f; r.beta = 0.f;
-  na2 = na; nb2 = nb; Dp2 = Dp; Dpi2 = Dpi; Dq2 = Dq; Dqi2 = Dqi;
-  const float d = dhat * Dp * Dq;
-  const float ab = na * nb;
-  const bool rot = have && d * d > kPreTol2 * ab && ab > 1e-25f;
-  if (have && d * d > kPreBig2 * ab) big = 1;
-  if (__any_sync(kFull, rot)) {   // warp-uniform set-up, as in cb_params
-    const float num = nb - na, den = 2.f * d;
+// Threshold test and rotation set-up of one pair (p, q) from the true norms and the scaled dot product; updates the two
+// column records and returns (-alpha, -alpha, beta, beta), zeros when the pair is not rotated.
+__device__ __forceinline__ float4 p32_params(float dhat, P32Col& p, P32Col& q, int& big) {
+  const float d = dhat * p.d * q.d;
+  const float ab = p.n * q.n;
+  const bool rot = d * d > kPreTol2 * ab && ab > 1e-25f;
+  if (d * d > kPreBig2 * ab) big = 1;
+  float alpha = 0.f, beta = 0.f;
+  if (__any_sync(kFull, rot)) {   // warp-uniform set-up; lanes below the threshold discard it
+    const float num = q.n - p.n, den = 2.f * d;
     const float im = rcp_approx(fmaxf(fabsf(num), fabsf(den)));
     const float n1 = fabsf(num) * im, d1 = fabsf(den) * im;      // the larger one is 1
     const float S = fmaf(n1, n1, d1 * d1);                       // in [1, 2]
@@ -94,99 +96,42 @@ __device__ __forceinline__ P32Rot p32_params(float dhat, float na, float nb, flo
     float c = rsqrt_approx(w);
     c = c * fmaf(-0.5f * w * c, c, 1.5f);                        // one Newton step: V0 stays orthogonal to ~1e-5 over a run
     const float rc = w * c;
-    const float na_r = fmaxf(fmaf(-t, d, na), 0.f), nb_r = fmaxf(fmaf(t, d, nb), 0.f);
-    r.alpha = rot ? t * Dq * Dpi : 0.f;
-    r.beta = rot ? t * Dp * Dqi : 0.f;
-    Dp2 = rot ? c * Dp : Dp; Dq2 = rot ? c * Dq : Dq; Dpi2 = rot ? rc * Dpi : Dpi; Dqi2 = rot ? rc * Dqi : Dqi;
-    na2 = rot ? na_r : na;
-    nb2 = rot ? nb_r : nb;
-  }
-  return r;
-}
-
-// (p, q) -> (p - alpha q, q + beta p) on both rows at once, stored exchanged
-__device__ __forceinline__ void rot_swap2(u64& xa, u64& xb, u64 nalpha2, u64 beta2) {
-  const u64 np = fma2(nalpha2, xb, xa);
-  const u64 nq = fma2(beta2, xa, xb);
-  xa = nq;
-  xb = np;
-}
-
-template <bool STEP_B>
-__device__ __forceinline__ void p32_step(P32State& st, float4* wcs, int warp, int lane, int& big) {
-  const int grp = lane >> 2;
-  float pd[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    if (!STEP_B) pd[j] = hsum2(mul2(st.g[2 * j], st.g[2 * j + 1]));
-    else if (j < 7) pd[j] = hsum2(mul2(st.g[2 * j + 1], st.g[2 * j + 2]));
-    else pd[j] = hsum2(mul2(st.g[15], st.xg));
-  }
-  const float dhat = reduce8f(pd, lane);
-  float na, nb, Dp, Dpi, Dq, Dqi;
-  bool have = true;
-  if (!STEP_B) { na = st.e; nb = st.o; Dp = st.de; Dpi = st.dei; Dq = st.dq; Dqi = st.dqi; }
-  else {
-    const float e_next = __shfl_down_sync(kFull, st.e, 4);
-    const float de_next = __shfl_down_sync(kFull, st.de, 4);
-    const float dei_next = __shfl_down_sync(kFull, st.dei, 4);
-    na = st.o; Dp = st.dq; Dpi = st.dqi;
-    nb = (grp < 7) ? e_next : st.xn;
-    Dq = (grp < 7) ? de_next : st.xd;
-    Dqi = (grp < 7) ? dei_next : st.xdi;
-    have = (grp < 7) || (warp < 3);
-  }
-  float na2, nb2, Dp2, Dpi2, Dq2, Dqi2;
-  const P32Rot r = p32_params(dhat, na, nb, Dp, Dpi, Dq, Dqi, have, na2, nb2, Dp2, Dpi2, Dq2, Dqi2, big);
-  if (!STEP_B) {
-    st.e = nb2; st.de = Dq2; st.dei = Dqi2;
-    st.o = na2; st.dq = Dp2; st.dqi = Dpi2;
-  } else {
-    const float n_prev = __shfl_up_sync(kFull, na2, 4);
-    const float d_prev = __shfl_up_sync(kFull, Dp2, 4);
-    const float di_prev = __shfl_up_sync(kFull, Dpi2, 4);
-    if (have) { st.o = nb2; st.dq = Dq2; st.dqi = Dqi2; }
-    if (grp > 0) { st.e = n_prev; st.de = d_prev; st.dei = di_prev; }
-    if (grp == 7 && have) { st.xn = na2; st.xd = Dp2; st.xdi = Dpi2; }
-  }
-  // (-alpha, -alpha, beta, beta) of the 8 pairs to every lane through a warp-private line: one LDS.128 per pair delivers
-  // both packed multipliers
-  __syncwarp();
-  if ((lane & 3) == 0) wcs[grp] = make_float4(-r.alpha, -r.alpha, r.beta, r.beta);
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const float4 ab = wcs[j];
-    const u64 na2p = pack2(ab.x, ab.y), b2p = pack2(ab.z, ab.w);
-    if (!STEP_B) {
-      rot_swap2(st.g[2 * j], st.g[2 * j + 1], na2p, b2p);
-      rot_swap2(st.v[2 * j], st.v[2 * j + 1], na2p, b2p);
-    } else if (j < 7) {
-      rot_swap2(st.g[2 * j + 1], st.g[2 * j + 2], na2p, b2p);
-      rot_swap2(st.v[2 * j + 1], st.v[2 * j + 2], na2p, b2p);
-    } else if (warp < 3) {
-      rot_swap2(st.g[15], st.xg, na2p, b2p);
-      rot_swap2(st.v[15], st.xv, na2p, b2p);
+    if (rot) {
+      alpha = t * q.d * p.di;
+      beta = t * p.d * q.di;
+      p.n = fmaxf(fmaf(-t, d, p.n), 0.f);                        // |c p - s q|^2 = |p|^2 - t d,  |s p + c q|^2 = |q|^2 + t d
+      q.n = fmaxf(fmaf(t, d, q.n), 0.f);
+      p.d *= c; q.d *= c; p.di *= rc; q.di *= rc;
     }
   }
+  return make_float4(-alpha, -alpha, beta, beta);
 }
 
-constexpr int kPreXS = 68;   // u64 per exchange record: 32 g + 32 v + (norm, D, 1/D) + pad
+// (p, q) -> (p - alpha q, q + beta p) on both rows at once
+__device__ __forceinline__ void rot2(u64& p, u64& q, u64 nalpha2, u64 beta2) {
+  const u64 np = fma2(nalpha2, q, p);
+  q = fma2(beta2, p, q);
+  p = np;
+}
+
+constexpr size_t kPreSmem = 4 * 2 * 16 * 32 * sizeof(u64) + 4 * 16 * sizeof(float) + 4 * 8 * sizeof(float4) + 4 * sizeof(double);
 
 // One CTA (4 warps) per matrix.  V0 (FP32, row-major [component][column slot]) is the only result.
 __global__ void __launch_bounds__(128, 4)
 svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t batch, unsigned long long* sweep_sum) {
-  __shared__ __align__(16) u64 xch[2 * 4 * kPreXS];
-  __shared__ __align__(16) float4 wcs_all[4 * 8];
-  __shared__ double red[4];
+  extern __shared__ __align__(16) unsigned char pre_smem[];
+  u64* xbuf = reinterpret_cast<u64*>(pre_smem);                       // [warp][block A/B][g 8 slots, v 8 slots][lane]
+  float* nbuf = reinterpret_cast<float*>(xbuf + 4 * 2 * 16 * 32);      // [warp][16] norms travelling with the blocks
+  float4* wcs_all = reinterpret_cast<float4*>(nbuf + 4 * 16);          // [warp][8] multipliers of the current step
+  double* red = reinterpret_cast<double*>(wcs_all + 4 * 8);
   const int64_t m = blockIdx.x;
   if (m >= batch) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2;
   const double* a_in = A + m * 4096;
   float4* wcs = wcs_all + 8 * warp;
-  float* wsc = reinterpret_cast<float*>(wcs);   // the same 128 bytes hold the 16 slot scales between sweeps
+  float* wsc = reinterpret_cast<float*>(wcs);   // the same 128 bytes hold the 16 slot scales when a round is folded
 
-  P32State st;
+  u64 ga[8], gb[8], va[8], vb[8];
   {
     double t0[16], t1[16];
     double amax = 0.0;
@@ -207,24 +152,25 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
     double pre = 1.0;
     if (amax > 0.0 && amax < CUDART_INF) { const int e = -ilogb(amax); pre = scalbn(1.0, e > 1000 ? 1000 : e); }
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-      st.g[s] = pack2((float)(t0[s] * pre), (float)(t1[s] * pre));
-      st.v[s] = pack2((16 * warp + s == lane) ? 1.f : 0.f, (16 * warp + s == lane + 32) ? 1.f : 0.f);
+    for (int i = 0; i < 8; i++) {
+      ga[i] = pack2((float)(t0[i] * pre), (float)(t1[i] * pre));
+      gb[i] = pack2((float)(t0[8 + i] * pre), (float)(t1[8 + i] * pre));
+      va[i] = pack2((16 * warp + i == lane) ? 1.f : 0.f, (16 * warp + i == lane + 32) ? 1.f : 0.f);
+      vb[i] = pack2((16 * warp + 8 + i == lane) ? 1.f : 0.f, (16 * warp + 8 + i == lane + 32) ? 1.f : 0.f);
     }
   }
-  st.xg = st.xv = 0ull;
-  st.xn = 0.f; st.xd = st.xdi = 1.f;
+  const int next_grp_lane = (((grp + 1) & 7) << 2) | (lane & 3);
 
   int sweeps = 0;
   bool more = true;
   while (sweeps < kPreMaxSweeps && more) {
     sweeps++;
     int big = 0;
-    st.de = st.dei = st.dq = st.dqi = 1.f;
-    {  // exact slot norms: 16 values -> 2 per 4-lane group
+    P32Col ca, cb;   // A-slot grp, and the B-slot this group currently plays against (B-slot grp between rounds)
+    {  // exact norms: 16 values -> (A-slot grp, B-slot grp) in every lane of group grp
       float n2[16];
 #pragma unroll
-      for (int s = 0; s < 16; s++) n2[s] = hsum2(mul2(st.g[s], st.g[s]));
+      for (int i = 0; i < 8; i++) { n2[2 * i] = hsum2(mul2(ga[i], ga[i])); n2[2 * i + 1] = hsum2(mul2(gb[i], gb[i])); }
       halvef<16>(n2, (lane & 16) != 0, 16);
       float h8[8];
 #pragma unroll
@@ -235,61 +181,128 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
       float e = h4[0], o = h4[1];
       e += __shfl_xor_sync(kFull, e, 2); o += __shfl_xor_sync(kFull, o, 2);
       e += __shfl_xor_sync(kFull, e, 1); o += __shfl_xor_sync(kFull, o, 1);
-      st.e = e; st.o = o;
+      ca.n = e; cb.n = o;
     }
+    ca.d = ca.di = cb.d = cb.di = 1.f;
+
 #pragma unroll 1
-    for (int sp2 = 0; sp2 < 32; sp2++) {
-      p32_step<false>(st, wcs, warp, lane, big);
-      u64* out = xch + warp * kPreXS;   // hand my first column to the left neighbour for the B step
-      if (warp > 0) {
-        out[lane] = st.g[0]; out[32 + lane] = st.v[0];
-        if (lane == 0) { float* sc = reinterpret_cast<float*>(out + 64); sc[0] = st.e; sc[1] = st.de; sc[2] = st.dei; }
-      }
-      __syncthreads();
-      if (warp < 3) {
-        const u64* in = xch + (warp + 1) * kPreXS;
-        st.xg = in[lane]; st.xv = in[32 + lane];
-        const float* sc = reinterpret_cast<const float*>(in + 64);
-        st.xn = sc[0]; st.xd = sc[1]; st.xdi = sc[2];
-      }
-      p32_step<true>(st, wcs, warp, lane, big);
-      u64* out2 = xch + 4 * kPreXS + (warp + 1) * kPreXS;   // give the borrowed (rotated) column back
-      if (warp < 3) {
-        out2[lane] = st.xg; out2[32 + lane] = st.xv;
-        if (lane == 28) { float* sc = reinterpret_cast<float*>(out2 + 64); sc[0] = st.xn; sc[1] = st.xd; sc[2] = st.xdi; }
-      }
-      __syncthreads();
-      if (warp > 0) {
-        const u64* in2 = xch + 4 * kPreXS + warp * kPreXS;
-        st.g[0] = in2[lane]; st.v[0] = in2[32 + lane];
-        if (grp == 0) { const float* sc = reinterpret_cast<const float*>(in2 + 64); st.e = sc[0]; st.de = sc[1]; st.dei = sc[2]; }
-      }
-    }
-    // fold the scales back into the columns
-    __syncwarp();
-    if ((lane & 3) == 0) { wsc[2 * grp] = st.de; wsc[2 * grp + 1] = st.dq; }
-    __syncwarp();
+    for (int round = 0; round < 7; round++) {
+      if (round == 0) {
+        // pairs inside the blocks: step m pairs slot i with slot i xor m.  Groups i < i^m take the pair of block A, groups
+        // i > i^m that of block B; the partner group's record of the other column comes and goes by shuffles.
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-      const float D = wsc[s];
-      const u64 D2 = pack2(D, D);
-      st.g[s] = mul2(st.g[s], D2);
-      st.v[s] = mul2(st.v[s], D2);
+        for (int msk = 1; msk < 8; msk++) {
+          float pd[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            pd[j] = (j < (j ^ msk)) ? hsum2(mul2(ga[j], ga[j ^ msk])) : hsum2(mul2(gb[j ^ msk], gb[j]));
+          const float dhat = reduce8f(pd, lane);
+          const bool lower = grp < (grp ^ msk);
+          P32Col rem;   // lower: the partner's A record (= q);  upper: the partner's B record (= p)
+          rem.n = __shfl_xor_sync(kFull, lower ? cb.n : ca.n, 4 * msk);
+          rem.d = __shfl_xor_sync(kFull, lower ? cb.d : ca.d, 4 * msk);
+          rem.di = __shfl_xor_sync(kFull, lower ? cb.di : ca.di, 4 * msk);
+          P32Col p = lower ? ca : rem, q = lower ? rem : cb;
+          const float4 mult = p32_params(dhat, p, q, big);
+          if (lower) ca = p; else cb = q;
+          const P32Col back = lower ? q : p;
+          rem.n = __shfl_xor_sync(kFull, back.n, 4 * msk);
+          rem.d = __shfl_xor_sync(kFull, back.d, 4 * msk);
+          rem.di = __shfl_xor_sync(kFull, back.di, 4 * msk);
+          if (lower) cb = rem; else ca = rem;
+          __syncwarp();
+          if ((lane & 3) == 0) wcs[grp] = mult;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 ab = wcs[j];
+            const u64 na2 = pack2(ab.x, ab.y), b2 = pack2(ab.z, ab.w);
+            if (j < (j ^ msk)) { rot2(ga[j], ga[j ^ msk], na2, b2); rot2(va[j], va[j ^ msk], na2, b2); }
+            else { rot2(gb[j ^ msk], gb[j], na2, b2); rot2(vb[j ^ msk], vb[j], na2, b2); }
+          }
+        }
+      }
+      // the 64 pairs between the two blocks
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        float pd[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) pd[i] = hsum2(mul2(ga[i], gb[(i + s) & 7]));
+        const float dhat = reduce8f(pd, lane);
+        const float4 mult = p32_params(dhat, ca, cb, big);
+        // group g played B-slot (g + s) mod 8; in the next step that slot belongs to group g - 1
+        cb.n = __shfl_sync(kFull, cb.n, next_grp_lane);
+        cb.d = __shfl_sync(kFull, cb.d, next_grp_lane);
+        cb.di = __shfl_sync(kFull, cb.di, next_grp_lane);
+        __syncwarp();
+        if ((lane & 3) == 0) wcs[grp] = mult;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float4 ab = wcs[i];
+          const u64 na2 = pack2(ab.x, ab.y), b2 = pack2(ab.z, ab.w);
+          rot2(ga[i], gb[(i + s) & 7], na2, b2);
+          rot2(va[i], vb[(i + s) & 7], na2, b2);
+        }
+      }
+      // fold the scales back into the columns (after eight ownership moves group g holds B-slot g again)
+      __syncwarp();
+      if ((lane & 3) == 0) { wsc[grp] = ca.d; wsc[8 + grp] = cb.d; }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float da = wsc[i], db = wsc[8 + i];
+        const u64 da2 = pack2(da, da), db2 = pack2(db, db);
+        ga[i] = mul2(ga[i], da2); va[i] = mul2(va[i], da2);
+        gb[i] = mul2(gb[i], db2); vb[i] = mul2(vb[i], db2);
+      }
+      ca.d = ca.di = cb.d = cb.di = 1.f;
+      // the blocks move one position on: position 0 (warp 0's A) stays, 1 -> 2 -> ... -> 7 -> 1, warp w holding positions w (A)
+      // and 7 - w (B).  New A of warp 1 = old B of warp 0, of warps 2, 3 = old A of the warp before; new B of warps 0..2 =
+      // old B of the next warp, of warp 3 = its own old A.
+      {
+        u64* mine = xbuf + warp * (2 * 16 * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          mine[i * 32 + lane] = ga[i]; mine[(8 + i) * 32 + lane] = va[i];
+          mine[(16 + i) * 32 + lane] = gb[i]; mine[(24 + i) * 32 + lane] = vb[i];
+        }
+        if ((lane & 3) == 0) { nbuf[warp * 16 + grp] = ca.n; nbuf[warp * 16 + 8 + grp] = cb.n; }
+        __syncthreads();
+        if (warp > 0) {
+          const int sw = warp - 1, sb = (warp == 1) ? 1 : 0;
+          const u64* src = xbuf + sw * (2 * 16 * 32) + sb * (16 * 32);
+#pragma unroll
+          for (int i = 0; i < 8; i++) { ga[i] = src[i * 32 + lane]; va[i] = src[(8 + i) * 32 + lane]; }
+          ca.n = nbuf[sw * 16 + sb * 8 + grp];
+        }
+        {
+          const int sw = (warp < 3) ? warp + 1 : 3, sb = (warp < 3) ? 1 : 0;
+          const u64* src = xbuf + sw * (2 * 16 * 32) + sb * (16 * 32);
+#pragma unroll
+          for (int i = 0; i < 8; i++) { gb[i] = src[i * 32 + lane]; vb[i] = src[(8 + i) * 32 + lane]; }
+          cb.n = nbuf[sw * 16 + sb * 8 + grp];
+        }
+        __syncthreads();
+      }
     }
-    __syncwarp();
     more = __syncthreads_or(big) != 0;
   }
   if (tid == 0 && sweep_sum) atomicAdd(sweep_sum, (unsigned long long)sweeps);
 
+  // the column order of V0 is the final arrangement of the blocks; G1 = A V1 inherits it and the epilogue of the FP64
+  // kernel sorts by singular value anyway
   float* v_out = V0 + m * 4096;
 #pragma unroll
-  for (int s = 0; s < 16; s += 4) {
-    float lo[4], hi[4];
+  for (int h = 0; h < 2; h++)
 #pragma unroll
-    for (int k = 0; k < 4; k++) unpack2(st.v[s + k], lo[k], hi[k]);
-    *reinterpret_cast<float4*>(v_out + lane * 64 + 16 * warp + s) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<float4*>(v_out + (lane + 32) * 64 + 16 * warp + s) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  }
+    for (int s = 0; s < 8; s += 4) {
+      float lo[4], hi[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) unpack2(h ? vb[s + k] : va[s + k], lo[k], hi[k]);
+      *reinterpret_cast<float4*>(v_out + lane * 64 + 16 * warp + 8 * h + s) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<float4*>(v_out + (lane + 32) * 64 + 16 * warp + 8 * h + s) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -441,10 +454,11 @@ cudaError_t launch_svd64_pre(cudaStream_t s, const double* A, int64_t batch, dou
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(svd64_ortho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrthoSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(svd64_pre32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPreSmem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  svd64_pre32_kernel<<<(unsigned)batch, 128, 0, s>>>(A, v0, batch, sweep_sum);
+  svd64_pre32_kernel<<<(unsigned)batch, 128, kPreSmem, s>>>(A, v0, batch, sweep_sum);
   svd64_ortho_kernel<<<(unsigned)batch, 256, kOrthoSmem, s>>>(A, v0, g1, v1, batch);
   *G1 = g1;
   *V1 = v1;
