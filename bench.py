@@ -412,10 +412,16 @@ def host_case(name, nd, units, pinned=True):
 def time_host(call, steps, sync):
     t0 = time.perf_counter()
     res = None
+    per = []
     for _ in range(steps):
+        t1 = time.perf_counter()
         res = call()
+        per.append(round(1e3 * (time.perf_counter() - t1), 2))
     sync()
-    return time.perf_counter() - t0, res
+    dt = time.perf_counter() - t0
+    if os.environ.get("BENCH_DEBUG"):
+        sys.stderr.write("time_host per-call ms: %s\n" % per)
+    return dt, res
 
 
 def fp64_peaks(lib, dev):
@@ -583,8 +589,9 @@ def run_ours(args):
     # ---------------- end to end through the operator (nd4js_b200.la.*), pinned and pageable ----------------
     call, h2d, d2h, sample = host_case(args.workload, nd, units, pinned=True)
     e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(2):
-        call()
+    last = None
+    for _ in range(3):   # warm-up as the timed loop runs: the previous result is still referenced while the next call allocates
+        last = call()    # its own, so the pinned-block cache ends up holding the two blocks the steady state alternates between
     s0 = nd.stats()
     barrier()
     e2e_secs, last = time_host(call, e2e_steps, sync)
@@ -597,9 +604,10 @@ def run_ours(args):
     if rank == 0:
         ins_s, outs_s = sample(last)
         parity["e2e"] = parity_of(args.workload, ins_s, outs_s)
-    del call, sample, last
+    del call, sample
     pcall, _, _, _ = host_case(args.workload, nd, units, pinned=False)
-    pcall()
+    last = pcall()
+    last = pcall()
     barrier()
     page_steps = max(1, min(args.steps, 3))
     page_secs, _ = time_host(pcall, page_steps, sync)
@@ -692,7 +700,8 @@ def run_ours(args):
             nd._lib.check(lib.nd4b_shutdown())
             nd.init(list(range(world)))
             call, h2d_s, d2h_s, sample = host_case(args.workload, nd, units, pinned=True)
-            call()
+            last = call()
+            last = call()
             t_sh, last = time_host(call, e2e_steps, lambda: None)
             ins_s, outs_s = sample(last)
             par = parity_of(args.workload, ins_s, outs_s)

@@ -382,7 +382,7 @@ struct CbRot { double alpha, beta; };
 // Outputs the scaled-rotation multipliers, and the norms/scales of the two columns AFTER the rotation (before exchange).
 __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, double Dp, double Dpi, double Dq, double Dqi,
                                            bool have, double tol2, double& na2, double& nb2, double& Dp2, double& Dpi2,
-                                           double& Dq2, double& Dqi2, int& rotated) {
+                                           double& Dq2, double& Dqi2, int& rotated, int& unsafe) {
   CbRot r;
   r.alpha = 0.0; r.beta = 0.0;
   na2 = na; nb2 = nb; Dp2 = Dp; Dpi2 = Dpi; Dq2 = Dq; Dqi2 = Dqi;
@@ -390,7 +390,8 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
   // The set-up runs warp-uniformly (if any pair of the warp rotates, every lane executes it and pairs below the threshold
   // discard the result with selects): a divergent branch here costs a reconvergence barrier in every step.
   // both squared norms above kNormMin = 2^-400, as one integer compare of the high words (they are never negative)
-  const bool rot = have && d * d > tol2 * na * nb && min(__double2hiint(na), __double2hiint(nb)) > 0x26f00000;
+  const double dd = d * d, thr = tol2 * na * nb;
+  const bool rot = have && dd > thr && min(__double2hiint(na), __double2hiint(nb)) > 0x26f00000;
   if (__any_sync(kFull, rot)) {
     const double num = nb - na, den = 2.0 * d;
 #ifndef ND4B_SVD_T_FP64
@@ -462,6 +463,20 @@ __device__ __forceinline__ CbRot cb_params(double dhat, double na, double nb, do
     na2 = rot ? na_r : na;
     nb2 = rot ? nb_r : nb;
     rotated = 1;
+    // Quadratic-convergence exit.  With p' = c p - s q, the cosine of p' with any third column r changes by
+    // s cos(q, r) |q| / |p'| (and that of q' by s cos(p, r) |p| / |q'|): at most tau = |t| max(|q|/|p|, |p|/|q|) times the
+    // largest cosine present, and a column takes part in 63 rotations per sweep.  So when 126 * max tau * max|cos| over
+    // the pairs rotated in a sweep stays below 64 eps, no cosine can exceed 64 eps afterwards — exactly what the
+    // confirming sweep would establish — and that sweep is not run.  (For columns of very different norms tau is about
+    // the cosine itself, not t: a null column of a rank-deficient matrix keeps the confirming sweep.)  The two maxima
+    // are tracked as integers, on the high words: tol2 = 2^-92, so hi(d^2) - hi(thr) is 2^20 (log2 cos^2 + 92), hi(|t|)
+    // is 2^20 (log2 |t| + 1023) and |hi(|q|^2) - hi(|p|^2)| / 2 is 2^20 log2 of the norm ratio; `unsafe` packs the cos^2
+    // term in the upper and the tau term in the lower 16 bits, in sixteenths of a binade (test: svd64cb_kernel).
+    if (rot) {
+      const int e1 = max(__double2hiint(dd) - __double2hiint(thr), 0) >> 16;                       // 16 (log2 cos^2 + 92), >= 0 when rotated
+      const int e2 = max((__double2hiint(t) & 0x7fffffff) - 0x3c000000 + (abs(__double2hiint(nb) - __double2hiint(na)) >> 1), 0) >> 16;   // 16 (log2 tau + 63)
+      unsafe = max(unsafe & 0xffff0000, e1 << 16) | max(unsafe & 0xffff, min(e2, 0xffff));
+    }
   }
   return r;
 }
@@ -488,7 +503,7 @@ __device__ __forceinline__ void fast_rot_swap(double& xa, double& xb, double alp
 }
 
 template <bool STEP_B>
-__device__ __forceinline__ void cb_step(CbState& st, double2* wcs, int warp, int lane, double tol2, int& rotated) {
+__device__ __forceinline__ void cb_step(CbState& st, double2* wcs, int warp, int lane, double tol2, int& rotated, int& unsafe) {
   const int grp = lane >> 2;
   // slot pairs of this step in register terms: A: (2j, 2j+1); B: (2j+1, 2j+2) with slot 16 = the borrowed column
   double pd[8];
@@ -513,7 +528,7 @@ __device__ __forceinline__ void cb_step(CbState& st, double2* wcs, int warp, int
     have = (grp < 7) || (warp < 3);                                // slot 64 does not exist
   }
   double na2, nb2, Dp2, Dpi2, Dq2, Dqi2;
-  const CbRot r = cb_params(dhat, na, nb, Dp, Dpi, Dq, Dqi, have, tol2, na2, nb2, Dp2, Dpi2, Dq2, Dqi2, rotated);
+  const CbRot r = cb_params(dhat, na, nb, Dp, Dpi, Dq, Dqi, have, tol2, na2, nb2, Dp2, Dpi2, Dq2, Dqi2, rotated, unsafe);
   // exchanged storage: first slot of the pair <- rotated q, second slot <- rotated p
   if (!STEP_B) {
     st.e = nb2; st.de = Dq2; st.dei = Dqi2;
@@ -635,7 +650,7 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
   bool converged = false;
   while (sweeps < kMaxSweeps && !converged) {
     sweeps++;
-    int rotated = 0;
+    int rotated = 0, unsafe = 0;
     st.de = st.dei = st.dq = st.dqi = 1.0;
     {  // exact slot norms: 16 values -> 2 per 4-lane group
       double n2[16];
@@ -655,7 +670,7 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
     }
 #pragma unroll 1
     for (int sp2 = 0; sp2 < N / 2; sp2++) {
-      cb_step<false>(st, wcs, warp, lane, tol2, rotated);
+      cb_step<false>(st, wcs, warp, lane, tol2, rotated, unsafe);
       // hand my first column (slot 16w) to the left neighbour for the B step
       double* out = xch + warp * XS;
       if (warp > 0) {
@@ -668,7 +683,7 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
         st.xg0 = in[lane]; st.xg1 = in[32 + lane]; st.xv0 = in[64 + lane]; st.xv1 = in[96 + lane];
         st.xn = in[128]; st.xd = in[129]; st.xdi = in[130];
       }
-      cb_step<true>(st, wcs, warp, lane, tol2, rotated);
+      cb_step<true>(st, wcs, warp, lane, tol2, rotated, unsafe);
       // give the borrowed (rotated) column back
       double* out2 = xch + 4 * XS + (warp + 1) * XS;
       if (warp < 3) {
@@ -692,7 +707,18 @@ svd64cb_kernel(const double* __restrict__ A, double* __restrict__ U, double* __r
       st.g0[s] *= D; st.g1[s] *= D; st.v0[s] *= D; st.v1[s] *= D;
     }
     __syncwarp();
-    converged = !__syncthreads_or(rotated);
+    {
+      // block maxima of the two terms (cb_params) — the maxima of different warps must be combined: one warp's largest |t| can
+      // meet another warp's largest cosine.  Converged when nothing was rotated, or when
+      // log2 max|cos| + log2 max|t| < log2(64 eps / 126) - margin = -55:  (e1/16 - 92)/2 + (e2/16 - 63) < -55, i.e. e1/2 + e2 < 864
+      const int m1 = __reduce_max_sync(kFull, (unsigned)unsafe >> 16), m2 = __reduce_max_sync(kFull, unsafe & 0xffff);
+      int* red = reinterpret_cast<int*>(sq);   // sq is idle between the prologue and the epilogue
+      if (lane == 0) { red[2 * warp] = m1; red[2 * warp + 1] = m2; }
+      const bool any_rot = __syncthreads_or(rotated) != 0;   // also orders the writes above before the reads below
+      const int b1 = max(max(red[0], red[2]), max(red[4], red[6])), b2 = max(max(red[1], red[3]), max(red[5], red[7]));
+      converged = !any_rot || (b1 >> 1) + b2 < 864;
+      __syncthreads();   // red is rewritten at the end of the next sweep only, but keep the two uses apart
+    }
   }
   if (tid == 0) {
     if (sweeps_out) atomicMax(sweeps_out, sweeps);
