@@ -126,7 +126,7 @@ class ClockSampler:
 
 
 KERNEL = {"c1": "gemm_pipe_kernel", "g4k": "gemm_pipe_kernel", "c2": "matmul32_kernel", "c2b": "matmul32_kernel", "c3": "chol16_kernel",
-          "c4": "qr64x32_blocked_kernel", "c5": "svd64cb_kernel", "s3": "trisolve16_kernel", "l4": "qr_lstsq32_kernel",
+          "c4": "qr64x32_blocked_kernel", "c5": "svd64_pre32_kernel + svd64_ortho_kernel + svd64cb_kernel", "s3": "trisolve16_kernel", "l4": "qr_lstsq32_kernel",
           "i4": "qr64x32_inplace_kernel", "v5": "svd_lstsq_kernel"}
 OPERATOR = {"c1": "matmul2", "c2": "matmul2", "c2b": "matmul2", "g4k": "matmul2", "c3": "cholesky_decomp", "c4": "qr_decomp",
             "c5": "svd_jac_1sided", "s3": "cholesky_solve", "l4": "qr_lstsq", "i4": "_qr_decomp_inplace", "v5": "svd_lstsq"}
@@ -289,6 +289,21 @@ class DeviceCase:
         if self.sweeps is None or not self.launches:
             return None
         return float(self.pre_sum.item()) / (self.launches * self.units)
+
+    def plain_sweeps(self):
+        """Mean sweeps of the plain FP64 iteration (no preconditioner: the launch gets no workspace) on the same input — the
+        work a pure-FP64 one-sided Jacobi needs, for the 'equivalent' roofline figure."""
+        L, p, t = self.lib, (lambda x: C.c_void_p(x.data_ptr())), self.torch
+        tmp = t.zeros(1, dtype=t.int64, device="cuda")
+        L.nd4b_dev_svd_sweep_counter(self.dev, p(tmp))
+        i, o = self.ins, self.out
+        rc = L.nd4b_dev_svd_jac1_f64(self.dev, C.c_void_p(t.cuda.current_stream().cuda_stream), p(i[0]), p(o[0]), p(o[1]), p(o[2]),
+                                     self.units, 64, 64, None, None, 0)
+        t.cuda.synchronize()
+        L.nd4b_dev_svd_sweep_counter(self.dev, p(self.sweep_sum))
+        if rc:
+            raise RuntimeError(L.nd4b_last_error().decode())
+        return float(tmp.item()) / self.units
 
     def close(self):
         if self.sweeps is not None:
@@ -571,6 +586,7 @@ def run_ours(args):
     flop_unit = fpu * (sweeps_mean if sweeps_mean else 1) + (4 * 2 * 64 ** 3 if pre_mean else 0)
     achieved_gbs = bpu * units / launch_s / 1e9
     parity = {"device_resident": case.parity()} if rank == 0 else {}
+    plain_mean = case.plain_sweeps() if pre_mean else None   # after the parity check: it overwrites the outputs
     case.close()
     del case
     torch.cuda.empty_cache()
@@ -581,7 +597,9 @@ def run_ours(args):
         if rank == 0:
             emit({"workload": args.workload, "ms_per_launch": 1e3 * launch_s, "ms_per_launch_sustained": 1e3 * long_secs / n_long,
                   "matrices_per_s": value, "gflops": value * flop_unit / 1e9, "hbm_gbs_algorithmic": achieved_gbs,
-                  "sweeps_max": sweeps, "sweeps_mean": sweeps_mean, "fp32_pre_sweeps_mean": pre_mean, "parity": parity})
+                  "sweeps_max": sweeps, "sweeps_mean": sweeps_mean, "fp32_pre_sweeps_mean": pre_mean,
+                  "plain_fp64_sweeps_mean": plain_mean,
+                  "frac_of_fp64_peak_equivalent": (value / world * fpu * plain_mean / 1e12 / fp64_peak) if plain_mean else None, "parity": parity})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -627,6 +645,12 @@ def run_ours(args):
                         "frac": tflops / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": "FP64 pipe peak " + fp64_src,
                         "kernel": KERNEL[args.workload], "algorithmic_flop_per_unit": flop_unit, "units_per_launch": units}
+            if plain_mean:
+                # the preconditioner moves most sweeps to FP32, so the FP64 flop actually executed understate the work done:
+                # `equivalent` charges the sweeps the plain FP64 iteration needs on the same input (measured in this run)
+                eq = value / world * fpu * plain_mean / 1e12
+                roofline["equivalent"] = {"plain_fp64_sweeps_mean": plain_mean, "tflops": eq, "frac": eq / fp64_peak,
+                                          "note": "matrices/s x (flop per sweep x sweeps of the plain FP64 one-sided Jacobi on the same input)"}
         else:
             roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
@@ -670,16 +694,20 @@ def run_ours(args):
             s2 = max_over_ranks(s2, device="cuda")
             sw = c2.mean_sweeps() or 1
             pre2 = c2.mean_pre_sweeps() if name == "c5" else None
+            par2 = c2.parity() if rank == 0 else None   # before plain_sweeps(), which overwrites the outputs
+            plain2 = c2.plain_sweeps() if pre2 else None
             gf = world * u2 * n2 / s2 * (f2 * sw + (4 * 2 * 64 ** 3 if pre2 else 0)) / 1e9
             gbs = b2 * u2 * n2 / s2 / 1e9
             others[name] = {"workload": d2, "matrices_per_s": world * u2 * n2 / s2, "ms_per_launch": 1e3 * s2 / n2,
                             "gflops": gf, "hbm_gbs_algorithmic": gbs,
                             "frac_of_hbm_peak": gbs / hbm_peak, "frac_of_fp64_peak": gf / world / 1e3 / fp64_peak,
                             "sweeps_mean": sw if name == "c5" else None, "fp32_pre_sweeps_mean": pre2,
+                            "plain_fp64_sweeps_mean": plain2,
+                            "frac_of_fp64_peak_equivalent": (u2 * n2 / s2 * f2 * plain2 / 1e12 / fp64_peak) if plain2 else None,
                             "sweeps_max": int(c2.sweeps[0].item()) if name == "c5" else None}
             if rank == 0:
-                others[name]["parity"] = c2.parity()
-                parity["others." + name] = others[name]["parity"]
+                others[name]["parity"] = par2
+                parity["others." + name] = par2
             c2.close()
             del c2
             torch.cuda.empty_cache()
