@@ -610,6 +610,7 @@ def run_ours(args):
     last = None
     for _ in range(3):   # warm-up as the timed loop runs: the previous result is still referenced while the next call allocates
         last = call()    # its own, so the pinned-block cache ends up holding the two blocks the steady state alternates between
+    last = None
     s0 = nd.stats()
     barrier()
     e2e_secs, last = time_host(call, e2e_steps, sync)
@@ -626,6 +627,7 @@ def run_ours(args):
     pcall, _, _, _ = host_case(args.workload, nd, units, pinned=False)
     last = pcall()
     last = pcall()
+    last = None
     barrier()
     page_steps = max(1, min(args.steps, 3))
     page_secs, _ = time_host(pcall, page_steps, sync)
@@ -730,6 +732,7 @@ def run_ours(args):
             call, h2d_s, d2h_s, sample = host_case(args.workload, nd, units, pinned=True)
             last = call()
             last = call()
+            last = None
             t_sh, last = time_host(call, e2e_steps, lambda: None)
             ins_s, outs_s = sample(last)
             par = parity_of(args.workload, ins_s, outs_s)
