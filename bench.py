@@ -574,7 +574,7 @@ def run_ours(args):
     barrier()
     secs = max_over_ranks(secs, device="cuda")
     # the same launch back to back for at least half a second: what the clocks settle to under a sustained load
-    n_long = max(args.steps, int(0.5 / max(secs / args.steps, 1e-6)) + 1)
+    n_long = max(args.steps, int(args.sustained_seconds / max(secs / args.steps, 1e-6)) + 1)
     long_secs = max_over_ranks(time_device(torch, case, n_long, 0), device="cuda")
     sweeps = int(case.sweeps[0].item()) if case.sweeps is not None else None
     sweeps_mean = case.mean_sweeps()
@@ -666,7 +666,7 @@ def run_ours(args):
                        if bpu * units > 200e6 else "working set fits L2: kernel-only figure is L2-warm, see e2e"},
             "gflops": value * flop_unit / 1e9,
             "sustained": {"value": world * units * n_long / long_secs, "ms_per_step": 1e3 * long_secs / n_long, "launches": n_long,
-                          "seconds": long_secs, "note": "the same launch back to back for >= 0.5 s, CUDA events, max over ranks"},
+                          "seconds": long_secs, "note": "the same launch back to back for >= %.2g s, CUDA events, max over ranks" % args.sustained_seconds},
             "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_secs / e2e_steps,
                     "timing": "host wall clock around the blocking operator call, barrier+sync both sides, max over ranks",
@@ -727,6 +727,14 @@ def run_ours(args):
         # through it; the other ranks wait on the host (gloo) so that nothing of theirs runs on the GPUs being timed
         dist.barrier(group=cpu_group)
         if rank == 0:
+            # the same call through the one-device context first, with the other ranks idle: the strong-scaling reference
+            call1, _, _, _ = host_case(args.workload, nd, units, pinned=True)
+            last = call1()
+            last = call1()
+            last = None
+            t_one, last = time_host(call1, e2e_steps, lambda: None)
+            del call1
+            last = None
             nd._lib.check(lib.nd4b_shutdown())
             nd.init(list(range(world)))
             call, h2d_s, d2h_s, sample = host_case(args.workload, nd, units, pinned=True)
@@ -739,9 +747,11 @@ def run_ours(args):
             parity["e2e_sharded"] = par
             line["e2e_sharded"] = {"value": units * e2e_steps / t_sh, "unit": "matrices/s", "n_devices": nd.stats()["n_devices"],
                                    "ms_per_step": 1e3 * t_sh / e2e_steps, "steps": e2e_steps,
-                                   "speedup_vs_one_device_call": (units * e2e_steps / t_sh) / (e2e_value / world),
+                                   "one_device_idle_box": {"value": units * e2e_steps / t_one, "ms_per_step": 1e3 * t_one / e2e_steps},
+                                   "speedup_vs_one_device_call": t_one / t_sh,
                                    "note": "one nd4js_b200.la.%s call of %d units from rank 0, its context over all %d devices "
-                                           "(contiguous shards, no collective); strong scaling of a single call" % (OPERATOR[args.workload], units, world)}
+                                           "(contiguous shards, no collective), against the same call through a one-device context "
+                                           "with the other ranks idle: strong scaling of a single call" % (OPERATOR[args.workload], units, world)}
             del call, sample, last
         dist.barrier(group=cpu_group)
 
@@ -805,6 +815,8 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the kernel-only lines of the other configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the c5_sharded and e2e_sharded legs")
+    ap.add_argument("--sustained-seconds", type=float, default=0.5,
+                    help="length of the back-to-back timing next to the K-step figure (shorten it for an ncu launch list)")
     ap.add_argument("--kernel-only", action="store_true", help="tuning aid: print the device-resident timing only")
     ap.add_argument("--no-fp64-probes", dest="fp64_probes", action="store_false",
                     help="do not measure the DFMA/DMMA pipe peaks in this run (use the recorded 37.15 TFLOP/s)")

@@ -392,6 +392,146 @@ static cudaError_t launch_pipe(cudaStream_t s, const double* A, const double* B,
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same pipelined GEMM fed by the TMA engine: a producer warp issues bulk asynchronous copies (cp.async.bulk, SASS
+// UBLKCP: one per tile row, 16-byte aligned, landing in the same padded, bank-conflict-free rows the DMMA fragments are
+// read from) and signals a per-stage "full" mbarrier through the copies' transaction bytes; the consumer warps wait on
+// it, run the DMMA k-steps of the stage and arrive on the stage's "empty" mbarrier, which the producer waits on before it
+// refills the stage.  No consumer thread issues a load instruction or a CTA-wide barrier inside the main loop.  Tensor-map
+// copies (cp.async.bulk.tensor) would land the tile densely: with 8-byte fragment reads neither the dense layout nor the
+// hardware swizzles are conflict-free for the B operand, which is why the rows are copied one by one into padded rows.
+// For full tiles only (I % BM == 0, J % BN == 0, K % BK == 0: C1, the 4096^3 probe); other shapes take gemm_pipe_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mb, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mb, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mb) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nGB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra GB_WAIT;\n}" ::"r"(mb), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mb) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
+
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
+__global__ void __launch_bounds__(WR * WC * 32 + 32)
+gemm_bulk_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                 int64_t batch, int I, int K, int J, BatchMap map, int tiles_m, int tiles_n) {
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, NCW = WR * WC;
+  extern __shared__ __align__(16) double gemm_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  int64_t tile = blockIdx.x;
+  const int tn = (int)(tile % tiles_n); tile /= tiles_n;
+  const int tm = (int)(tile % tiles_m); tile /= tiles_m;
+  const int64_t m = tile;
+  if (m >= batch) return;
+  int64_t ao, bo;
+  decode_batch(map, m, ao, bo);
+  const int row0 = tm * BM, col0 = tn * BN;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(gemm_smem);
+  const uint32_t bar_base = smem_base + (uint32_t)(STAGES * Cfg::STAGE_DOUBLES) * 8u;   // full[STAGES], empty[STAGES]
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; st++) { mbar_init(bar_base + 8u * st, 1); mbar_init(bar_base + 8u * (STAGES + st), NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nk = K / BK;
+
+  if (warp == NCW) {
+    // ---- producer warp: one bulk copy per tile row ----
+    const double* a = A + ao + (int64_t)row0 * K;
+    const double* b = B + bo + col0;
+    for (int kt = 0; kt < nk; kt++) {
+      const int st = kt % STAGES;
+      if (kt >= STAGES) mbar_wait(bar_base + 8u * (STAGES + st), ((kt / STAGES) - 1) & 1);   // the consumers have drained the stage
+      const uint32_t full = bar_base + 8u * st;
+      if (lane == 0) mbar_expect_tx(full, (uint32_t)((BM * BK + BK * BN) * 8));
+      __syncwarp();
+      const uint32_t as = smem_base + (uint32_t)(st * Cfg::STAGE_DOUBLES) * 8u, bs = as + (uint32_t)(BM * LDA) * 8u;
+      const int k0 = kt * BK;
+      for (int r = lane; r < BM; r += 32) bulk_g2s(as + (uint32_t)(r * LDA) * 8u, a + (int64_t)r * K + k0, BK * 8, full);
+      for (int r = lane; r < BK; r += 32) bulk_g2s(bs + (uint32_t)(r * LDB) * 8u, b + (int64_t)(k0 + r) * J, BN * 8, full);
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp / WC, wc = warp % WC;
+  double acc[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int kt = 0; kt < nk; kt++) {
+    const int st = kt % STAGES;
+    mbar_wait(bar_base + 8u * st, (kt / STAGES) & 1);
+    const double* as = gemm_smem + st * Cfg::STAGE_DOUBLES + (wr * TM * 8 + g) * LDA + t;
+    const double* bs = gemm_smem + st * Cfg::STAGE_DOUBLES + BM * LDA + t * LDB + wc * TN * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double af[TM], bfr[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) af[i] = as[i * 8 * LDA + ks * 4];
+#pragma unroll
+      for (int j = 0; j < TN; j++) bfr[j] = bs[ks * 4 * LDB + j * 8];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bfr[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_base + 8u * (STAGES + st));   // this warp is done reading the stage
+  }
+  double* c = C + m * (int64_t)I * J;
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    const int gr = row0 + (wr * TM + i) * 8 + g;
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+      const int gc = col0 + (wc * TN + j) * 8 + 2 * t;
+      *reinterpret_cast<double2*>(c + (int64_t)gr * J + gc) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  }
+}
+
+static bool gemm_bulk_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* ev = getenv("ND4B_GEMM_TMA");
+    on = ev ? atoi(ev) : 1;   // 0: cp.async (LDGSTS) tiles for every shape, for A/B timing
+  }
+  return on != 0;
+}
+
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
+static cudaError_t launch_bulk_or_pipe(cudaStream_t s, const double* A, const double* B, double* C,
+                                       int64_t batch, int I, int K, int J, const BatchMap& map) {
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_>;
+  if (!gemm_bulk_enabled() || I % Cfg::BM || J % Cfg::BN || K % Cfg::BK)
+    return launch_pipe<WR, WC, TM, TN, STAGES, BK_>(s, A, B, C, batch, I, K, J, map);
+  const int tiles_m = I / Cfg::BM, tiles_n = J / Cfg::BN;
+  const int64_t grid = batch * tiles_m * tiles_n;
+  if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  auto kern = gemm_bulk_kernel<WR, WC, TM, TN, STAGES, BK_>;
+  constexpr size_t smem = Cfg::SMEM + 2 * STAGES * 8;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  kern<<<(unsigned)grid, Cfg::THREADS + 32, smem, s>>>(A, B, C, batch, I, K, J, map, tiles_m, tiles_n);
+  return cudaGetLastError();
+}
+
 template <int WR, int WC, int TM, int TN>
 static cudaError_t launch_tiled(cudaStream_t s, const double* A, const double* B, double* C,
                                 int64_t batch, int I, int K, int J, const BatchMap& map, bool vec) {
@@ -676,9 +816,9 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
     const int64_t t128 = batch * ((I + 127) / 128) * ((J + 127) / 128);
     const int64_t t64 = batch * ((I + 63) / 64) * ((J + 63) / 64);
     // BK = 32 halves the barriers per flop of the 128x128 configuration (4096^3: 32.2 vs 31.7 TFLOP/s)
-    if (I >= 96 && J >= 96 && t128 >= sm_count) return launch_pipe<2, 4, 8, 4, 3, 32>(s, A, B, C, batch, I, K, J, map);
+    if (I >= 96 && J >= 96 && t128 >= sm_count) return launch_bulk_or_pipe<2, 4, 8, 4, 3, 32>(s, A, B, C, batch, I, K, J, map);
     // 64x64 tiles from 1.5 CTAs per SM on (1024^3 = 256 tiles: 80 us vs 101 us with 64x32 tiles)
-    if (I >= 48 && J >= 48 && 2 * t64 >= 3LL * sm_count) return launch_pipe<2, 2, 4, 4, 4>(s, A, B, C, batch, I, K, J, map);
+    if (I >= 48 && J >= 48 && 2 * t64 >= 3LL * sm_count) return launch_bulk_or_pipe<2, 2, 4, 4, 4>(s, A, B, C, batch, I, K, J, map);
     if (I >= 48 && J >= 24) {
       // few tiles (e.g. one 512^3): 32x32 tiles with 4 warps of 16x16 put >= 2 CTAs on most SMs
       // measured on one 512^3: 64x32 tiles/4 warps 18.7 us, 64x32/8 warps 17.6 us, 32x32/4 warps (256 CTAs) 16.4 us;
@@ -687,8 +827,8 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
       // Split-K over a 2- or 4-CTA cluster with a DSMEM reduction (64x64 tiles, 128 / 256 CTAs) was built and measured:
       // 18.9 / 20.9 us — a 64x64 CTA of 4 warps alone on an SM runs its main loop at ~52 % of the DMMA peak.
       const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
-      if (t6432 < 2LL * sm_count) return launch_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
-      return launch_pipe<4, 1, 2, 4, 4>(s, A, B, C, batch, I, K, J, map);
+      if (t6432 < 2LL * sm_count) return launch_bulk_or_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
+      return launch_bulk_or_pipe<4, 1, 2, 4, 4>(s, A, B, C, batch, I, K, J, map);
     }
   }
   const int64_t t6464 = batch * ((I + 63) / 64) * ((J + 63) / 64);

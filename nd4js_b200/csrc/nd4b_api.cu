@@ -3,6 +3,7 @@
 // and the device-resident entry points.  No CPU compute path exists in this library.
 #include "../../include/nd4b.h"
 #include "kernels.h"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler injects itself
 
 #include <algorithm>
 #include <atomic>
@@ -152,6 +153,12 @@ struct Context {
   int last_sweeps = 0;
   CopyPool* pool = nullptr;   // created on first use of pageable memory
   double t_copy = 0, t_wait = 0, t_alloc = 0;  // seconds spent in staging copies / stream waits / (re)allocation (ND4B_TRACE)
+};
+
+// NVTX range around every host entry point (tracing): `nsys` / `ncu --nvtx` show nd4b_matmul_f64 ... as named ranges.
+struct Range {
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
 };
 
 struct Timer {
@@ -677,6 +684,7 @@ int nd4b_matmul_shape(const int32_t* a_shape, int a_ndim, const int32_t* b_shape
 int nd4b_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
                     const double* B, const int32_t* b_shape, int b_ndim,
                     double* C, const int32_t* c_shape, int c_ndim) {
+  Range nvtx_range("nd4b_matmul_f64");
   if (!A || !B || !C || !c_shape) return fail(ND4B_E_ARG, "matmul: null pointer");
   int32_t want[ND4B_MAX_NDIM];
   int want_nd = 0;
@@ -765,6 +773,7 @@ int nd4b_matmul_f64(const double* A, const int32_t* a_shape, int a_ndim,
 // result comes down.  Runs on the first device of the context (a chain is a dependent sequence, not a batch to shard).
 int nd4b_matmul_plan_f64(int n, const double* const* mats, const int32_t* const* shapes, const int* ndims,
                          const int32_t* plan, int plan_len, double* C, const int32_t* c_shape, int c_ndim) {
+  Range nvtx_range("nd4b_matmul_plan_f64");
   if (n < 1 || !mats || !shapes || !ndims || !plan || plan_len < 1 || !C || !c_shape) return fail(ND4B_E_ARG, "matmul_plan: bad argument");
   for (int i = 0; i < n; i++) {
     if (!mats[i] || !shapes[i]) return fail(ND4B_E_ARG, "matmul_plan: null operand %d", i);
@@ -838,6 +847,7 @@ int nd4b_matmul_plan_f64(int n, const double* const* mats, const int32_t* const*
 // ---- cholesky -----------------------------------------------------------------------------------
 
 int nd4b_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t* first_bad) {
+  Range nvtx_range("nd4b_cholesky_f64");
   if (first_bad) *first_bad = -1;
   if (!S || !L) return fail(ND4B_E_ARG, "cholesky: null pointer");
   if (batch < 1 || n < 1) return fail(ND4B_E_ARG, "cholesky: batch and n must be >= 1");
@@ -871,6 +881,7 @@ int nd4b_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_t*
 // ---- qr -----------------------------------------------------------------------------------------
 
 int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
+  Range nvtx_range("nd4b_qr_f64");
   if (!A || !Q || !R) return fail(ND4B_E_ARG, "qr: null pointer");
   if (batch < 1 || rows < 1 || cols < 1) return fail(ND4B_E_ARG, "qr: batch, rows and cols must be >= 1");
   Context* ctx;
@@ -887,6 +898,7 @@ int nd4b_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, 
 }
 
 int nd4b_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY, int64_t batch, int M, int N, int L) {
+  Range nvtx_range("nd4b_qr_inplace_f64");
   if (!A || !Y || !R || !QtY) return fail(ND4B_E_ARG, "qr_inplace: null pointer");
   if (batch < 1 || M < 1 || N < 1 || L < 1) return fail(ND4B_E_ARG, "qr_inplace: batch, M, N and L must be >= 1");
   Context* ctx;
@@ -903,6 +915,7 @@ int nd4b_qr_inplace_f64(const double* A, const double* Y, double* R, double* QtY
 // ---- qr_lstsq (src/la/qr.js:186-273), fused form for thin factors ------------------------------
 
 int nd4b_qr_lstsq_f64(const double* Q, const double* R, const double* Y, double* X, int64_t batch, int N, int M, int I, int J) {
+  Range nvtx_range("nd4b_qr_lstsq_f64");
   if (!Q || !R || !Y || !X) return fail(ND4B_E_ARG, "qr_lstsq: null pointer");
   if (batch < 1 || N < 1 || M < 1 || I < 1 || J < 1) return fail(ND4B_E_ARG, "qr_lstsq: batch, N, M, I and J must be >= 1");
   if (I > N) return fail(ND4B_E_ARG, "qr_lstsq(Q,R,y): Under-determined systems not supported. Use rrqr instead.");
@@ -922,6 +935,7 @@ int nd4b_qr_lstsq_f64(const double* Q, const double* R, const double* Y, double*
 
 int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
                       int64_t batch, int rows, int cols, int* sweeps_out) {
+  Range nvtx_range("nd4b_svd_jac1_f64");
   if (sweeps_out) *sweeps_out = 0;
   if (!A || !U || !sv || !V) return fail(ND4B_E_ARG, "svd_jac_1sided: null pointer");
   if (batch < 1 || rows < 1 || cols < 1) return fail(ND4B_E_ARG, "svd_jac_1sided: batch, rows and cols must be >= 1");
@@ -959,6 +973,7 @@ int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
 // ---- svd_rank / svd_lstsq / svd_solve (src/la/svd.js:31-226) -------------------------------------
 
 int nd4b_svd_rank_f64(const double* sv, int32_t* rank, int64_t batch, int n) {
+  Range nvtx_range("nd4b_svd_rank_f64");
   if (!sv || !rank) return fail(ND4B_E_ARG, "svd_rank: null pointer");
   if (batch < 1 || n < 1) return fail(ND4B_E_ARG, "svd_rank: batch and n must be >= 1");
   Context* ctx;
@@ -1036,6 +1051,7 @@ int nd4b_svd_lstsq_shape(const int32_t* u_shape, int u_ndim, const int32_t* sv_s
 int nd4b_svd_lstsq_f64(const double* U, const int32_t* u_shape, int u_ndim, const double* sv, const int32_t* sv_shape, int sv_ndim,
                        const double* V, const int32_t* v_shape, int v_ndim, const double* Y, const int32_t* y_shape, int y_ndim,
                        double* X, const int32_t* x_shape, int x_ndim) {
+  Range nvtx_range("nd4b_svd_lstsq_f64");
   if (!U || !sv || !V || !Y || !X || !x_shape) return fail(ND4B_E_ARG, "svd_lstsq: null pointer");
   Operand4 op[4] = {{u_shape, u_ndim, u_ndim - 2, 0, "U"}, {sv_shape, sv_ndim, sv_ndim - 1, 0, "sv"},
                     {v_shape, v_ndim, v_ndim - 2, 0, "V"}, {y_shape, y_ndim, y_ndim - 2, 0, "y"}};
@@ -1149,6 +1165,7 @@ int nd4b_svd_lstsq_f64(const double* U, const int32_t* u_shape, int u_ndim, cons
 int nd4b_tri_solve_f64(int op, const double* T, const int32_t* t_shape, int t_ndim,
                        const double* Y, const int32_t* y_shape, int y_ndim,
                        double* X, const int32_t* x_shape, int x_ndim) {
+  Range nvtx_range("nd4b_tri_solve_f64");
   static const char* who[3] = {"tril_solve(L,Y)", "triu_solve(U,Y)", "cholesky_solve(L,y)"};
   static const char* tn[3] = {"L", "U", "L"};
   if (op < 0 || op > 2) return fail(ND4B_E_ARG, "tri_solve: op must be 0, 1 or 2");
