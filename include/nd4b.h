@@ -37,7 +37,7 @@ extern "C" {
 #define ND4B_E_NAN_INPUT  (-7)  /* 'Assertion failed.' (KahanSum.set on NaN)        src/kahan_sum.js:29   */
 #define ND4B_E_ARG        (-8)  /* null pointer / non-positive dimension (NDArray rejects dims < 1, src/nd_array.js:138) */
 #define ND4B_E_CUDA       (-9)  /* CUDA runtime failure or no usable device; text in nd4b_last_error()     */
-#define ND4B_E_NO_CONVERGENCE (-10) /* Jacobi SVD hit the sweep limit (NaN/Inf input)                     */
+#define ND4B_E_NO_CONVERGENCE (-10) /* Jacobi SVD hit the sweep limit (60 sweeps; not seen on any input so far)  */
 #define ND4B_E_SINGULAR     1   /* 'Matrix contains NaNs or is (near) singular.'    src/la/cholesky.js:44 */
 
 #define ND4B_MAX_NDIM 32
@@ -130,7 +130,9 @@ int nd4b_qr_lstsq_f64(const double* Q, const double* R, const double* Y, double*
  *      ordering/sign rules src/la/_svd_jac_utils.js:123-188, shapes src/help.js:2321-2337 ------- */
 
 /* U[batch,rows,L], sv[batch,L] (descending, >= +0), V[batch,L,cols], L=min(rows,cols),
- * A = U diag(sv) V.  *sweeps_out (may be NULL): max Jacobi sweeps over the batch. */
+ * A = U diag(sv) V.  *sweeps_out (may be NULL): max Jacobi sweeps over the batch.  NaN / Infinity in a matrix gives NaN
+ * results for that matrix and ND4B_OK, as the reference's Jacobi loops do (every threshold test is false for NaN, so the
+ * iteration stops at once: svd_jac_2sided.js:112).  Singular values below 2^-200 of the largest are reported as 0. */
 int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
                       int64_t batch, int rows, int cols, int* sweeps_out);
 

@@ -500,20 +500,25 @@ gemm_bulk_kernel(const double* __restrict__ A, const double* __restrict__ B, dou
   }
 }
 
-static bool gemm_bulk_enabled() {
+static int gemm_bulk_mode() {
   static int on = -1;
   if (on < 0) {
     const char* ev = getenv("ND4B_GEMM_TMA");
-    on = ev ? atoi(ev) : 1;   // 0: cp.async (LDGSTS) tiles for every shape, for A/B timing
+    on = ev ? atoi(ev) : 1;   // 0: cp.async (LDGSTS) tiles for every shape; 1: bulk copies for 128x128 tiles; 2: for every full-tile shape
   }
-  return on != 0;
+  return on;
 }
 
 template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
 static cudaError_t launch_bulk_or_pipe(cudaStream_t s, const double* A, const double* B, double* C,
                                        int64_t batch, int I, int K, int J, const BatchMap& map) {
   using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_>;
-  if (!gemm_bulk_enabled() || I % Cfg::BM || J % Cfg::BN || K % Cfg::BK)
+  // Measured on B200 (tools/gemm_sweep.py, ND4B_GEMM_TMA=0/1): with 128x128x32 tiles (A rows of 256 B, B rows of 1 KiB) the
+  // bulk-copy pipeline equals the cp.async one (4096^3: 31.7 vs 32.2 TFLOP/s); with the small tiles of launch-sized
+  // products the per-row copies are 128 B each and the copy engine's latency per request dominates (512^3: 47 vs 17 us),
+  // so those keep cp.async unless ND4B_GEMM_TMA=2 forces the bulk path.
+  const int mode = gemm_bulk_mode();
+  if (mode == 0 || (mode == 1 && Cfg::BM < 128) || I % Cfg::BM || J % Cfg::BN || K % Cfg::BK)
     return launch_pipe<WR, WC, TM, TN, STAGES, BK_>(s, A, B, C, batch, I, K, J, map);
   const int tiles_m = I / Cfg::BM, tiles_n = J / Cfg::BN;
   const int64_t grid = batch * tiles_m * tiles_n;

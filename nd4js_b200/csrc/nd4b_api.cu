@@ -966,7 +966,7 @@ int nd4b_svd_jac1_f64(const double* A, double* U, double* sv, double* V,
   }
   ctx->last_sweeps = sweeps;
   if (sweeps_out) *sweeps_out = sweeps;
-  if (failed) return fail(ND4B_E_NO_CONVERGENCE, "svd_jac_1sided: no convergence within the sweep limit (NaN or Inf in A?)");
+  if (failed) return fail(ND4B_E_NO_CONVERGENCE, "svd_jac_1sided: no convergence within the sweep limit");
   return ND4B_OK;
 }
 
