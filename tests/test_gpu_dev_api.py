@@ -151,3 +151,63 @@ def test_ieee_fast_path_helpers_match_the_compiler(dev):
     bad_sqrt, bad_div, fast_sqrt, fast_div = (int(c) for c in counts)
     assert bad_sqrt == 0 and bad_div == 0, (bad_sqrt, bad_div)
     assert fast_sqrt > (1 << 27) and fast_div > (1 << 26), (fast_sqrt, fast_div)
+
+
+def test_dev_svd_preconditioned_pipeline_against_the_plain_iteration(dev, ref):
+    """64x64 with a workspace: FP32 Jacobi -> DMMA hand-over (V1 orthogonalised, G1 = A V1) -> FP64 Jacobi (csrc/svd_pre.cu);
+    without one: the plain FP64 iteration.  Both must satisfy the contract, agree on the singular values, and the
+    preconditioned run must need far fewer FP64 sweeps; a NaN matrix and a zero matrix in the batch take the hand-over's
+    fallback (A, I) without disturbing their neighbours."""
+    t = dev.torch
+    a = uniform(21, (40, 64, 64))
+    a[7] = 0.0
+    a[11, :, 5] = a[11, :, 3]                     # rank deficient
+    a[13] *= 2.0 ** 300
+    da = dev.up(a)
+    f64 = dict(dtype=t.float64, device="cuda")
+    outs = []
+    for with_ws in (True, False):
+        u, sv, v = t.empty(40, 64, 64, **f64), t.empty(40, 64, **f64), t.empty(40, 64, 64, **f64)
+        sweeps = t.zeros(1, dtype=t.int32, device="cuda")
+        ws = dev.lib.nd4b_dev_svd_workspace(40, 64, 64)
+        assert ws == 40 * (4096 * 4 + 2 * 4096 * 8)
+        work = t.empty(ws // 8, **f64)
+        dev.ok(dev.lib.nd4b_dev_svd_jac1_f64(0, dev.stream, dev.p(da), dev.p(u), dev.p(sv), dev.p(v), 40, 64, 64, dev.p(sweeps),
+                                             dev.p(work) if with_ws else None, ws if with_ws else 0))
+        outs.append((u.cpu().numpy(), sv.cpu().numpy(), v.cpu().numpy(), int(sweeps.item())))
+    (u1, s1, v1, sw1), (u0, s0, v0, sw0) = outs
+    assert sw1 <= 4 < sw0
+    for u, s, v in ((u1, s1, v1), (u0, s0, v0)):
+        rec = (u * s[:, None, :]) @ v
+        scale = np.maximum(np.sqrt(np.sum(a * a, axis=(1, 2))), 1e-300)
+        assert np.max(np.sqrt(np.sum((rec - a) ** 2, axis=(1, 2))) / scale) <= TOL
+        assert np.max(np.abs(np.swapaxes(u, 1, 2) @ u - np.eye(64))) <= TOL and np.max(np.abs(v @ np.swapaxes(v, 1, 2) - np.eye(64))) <= TOL
+        assert (np.diff(s, axis=-1) <= 0).all() and (s >= 0).all()
+    assert np.max(np.abs(s1 - s0) / np.maximum(s0[:, :1], 1e-300)) <= TOL
+    assert (s1[7] == 0).all() and s1[11, -1] <= 1e-12 * s1[11, 0]
+    _, sref, _ = ref.svd_jac_2sided(a[:4])
+    assert np.max(np.abs(s1[:4] - sref) / sref[:, :1]) <= TOL
+    an = a.copy()
+    an[3, 2, 2] = np.nan
+    dan = dev.up(an)
+    u, sv, v = t.empty(40, 64, 64, **f64), t.empty(40, 64, **f64), t.empty(40, 64, 64, **f64)
+    work = t.empty(dev.lib.nd4b_dev_svd_workspace(40, 64, 64) // 8, **f64)
+    dev.ok(dev.lib.nd4b_dev_svd_jac1_f64(0, dev.stream, dev.p(dan), dev.p(u), dev.p(sv), dev.p(v), 40, 64, 64, None, dev.p(work), work.numel() * 8))
+    sn = sv.cpu().numpy()
+    assert np.isnan(sn[3]).any()                                   # NaN in, NaN out for that matrix, as in the reference
+    assert (np.delete(sn, 3, axis=0) == np.delete(s1, 3, axis=0)).all()   # the neighbours are untouched, bit for bit
+
+
+def test_dev_matmul_bulk_copy_pipeline(dev, ref):
+    """Full 128x128x32 tiles on every SM: the GEMM fed by the TMA engine (gemm_bulk_kernel: producer warp, mbarrier ring,
+    cp.async.bulk per tile row)."""
+    t = dev.torch
+    a, b = uniform(31, (2048, 256)), uniform(32, (256, 2048))
+    da, db = dev.up(a), dev.up(b)
+    out = t.empty(2048, 2048, dtype=t.float64, device="cuda")
+    dev.ok(dev.lib.nd4b_dev_matmul_f64(0, dev.stream, dev.p(da), 0, dev.p(db), 0, dev.p(out), 1, 2048, 256, 2048))
+    rows = np.r_[0:8, 1020:1030, 2040:2048]
+    want = ref.matmul2(a[rows], b)
+    assert np.max(np.abs(out.cpu().numpy()[rows] - want) / (np.abs(a[rows]) @ np.abs(b))) <= TOL
+    got = out.cpu().numpy()
+    assert np.max(np.abs(got - a @ b)) <= 1e-11                    # every tile, against LAPACK-grade numpy
