@@ -192,7 +192,7 @@ __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* s
     }
     if (pad) rank = L + pads_before;
     perm[rank] = tid;
-    z = !(sj >= smax * kZeroRel) || !(sj >= DBL_MIN);
+    z = (sj < smax * kZeroRel) || (sj < DBL_MIN)   /* a NaN norm is not a zero: NaN in, NaN out */;
   }
   if (PADDED) __syncthreads();
   if (tid < N) {
@@ -861,7 +861,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
       smax = fmax(smax, sk);
     }
     perm[rank] = j;
-    zero_flag[j] = !(sj >= smax * kZeroRel) || !(sj >= DBL_MIN);
+    zero_flag[j] = (sj < smax * kZeroRel) || (sj < DBL_MIN)   /* a NaN norm is not a zero: NaN in, NaN out */;
     done_flag[j] = 0;
   }
   __syncthreads();
@@ -987,7 +987,7 @@ svd_tiny_kernel(const double* __restrict__ A, double* __restrict__ U, double* __
       int rank = 0;
       for (int k = 0; k < n; k++) rank += (sig[k] > sig[j]) || (sig[k] == sig[j] && k < j);
       permd[rank] = (double)j;
-      if (!(sig[j] >= smax * kZeroRel) || !(sig[j] >= DBL_MIN)) zero_mask |= 1u << j;
+      if (sig[j] < smax * kZeroRel || sig[j] < DBL_MIN) zero_mask |= 1u << j;
     }
     for (int j = 0; j < n; j++)
       if (!((zero_mask >> j) & 1)) {
