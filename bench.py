@@ -65,8 +65,9 @@ FP64_PEAK_TFLOPS = 37.15
 NCU_TRAFFIC_BYTES = {
     "c2": (1.577e9, "profiles/r01_ncu_c2_final.txt"),
     "c3": (1.014e9, "profiles/r01_ncu_c3_v3.txt"),
-    "c4": (2.800e9, "profiles/r01_ncu_c4_blocked.txt"),
-    "c5": (1.576e9, "profiles/r01_ncu_c5_v3.txt"),
+    "c4": (2.849e9, "profiles/r02_ncu_c4_blocked.txt"),
+    # three launches per call: FP32 Jacobi 0.774 GB, hand-over 1.824 GB, FP64 Jacobi 2.148 GB (V0, G1, V1 pass through HBM)
+    "c5": (4.746e9, "profiles/r02_ncu_c5_pipeline.txt"),
 }
 
 
