@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libnd4b.so")
+SO_PATH = os.environ.get("ND4B_LIB_PATH") or os.path.join(_HERE, "libnd4b.so")   # ND4B_LIB_PATH: an experimental build for A/B timing
 
 # symbols declared in include/nd4b.h (tests check that every one is exported)
 SYMBOLS = [

@@ -124,7 +124,13 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
 #pragma unroll
     for (int j = P; j < 8; j++) *reinterpret_cast<double2*>(xs + 8 * j + 2 * t) = make_double2(a[P][j][0], a[P][j][1]);
   }
-#pragma unroll 1
+#ifndef QB_PANEL_UNROLL
+#define QB_PANEL_UNROLL 2
+#endif
+  // two steps per trip: the parity of kk (pivot-column buffer, which of a lane's two rows is the pivot row) becomes a
+  // compile-time constant.  C4: 1.269 ms with 1, 1.233 with 2, 1.250 with 4, 1.376 with 8 (-DQB_PANEL_UNROLL for A/B builds)
+  constexpr int kPanelUnroll = QB_PANEL_UNROLL;
+#pragma unroll kPanelUnroll
   for (int kk = 0; kk < 8; kk++) {
     const double* xb = xs + 64 * (kk & 1);
     __syncwarp();
