@@ -1144,7 +1144,8 @@ cudaError_t launch_svd_jac1(cudaStream_t s, const double* A, double* U, double* 
       variant = ev ? atoi(ev) : 0;  // 1 = the shared-memory baseline kernel (kept for A/B profiling)
     }
     if (variant == 1) svd64_smem_kernel<<<(unsigned)batch, kSvd64Threads, kSvd64Smem, s>>>(A, U, sv, V, batch, sweeps, fail, ssum);
-    else if (svd_pre_enabled() && work != nullptr && work_bytes >= svd64_pre_workspace_bytes(batch)) {
+    else if (svd_pre_enabled() && work != nullptr && work_bytes >= svd64_pre_workspace_bytes(batch) &&
+             ((reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(A)) & 15) == 0) {   // 16-byte vector accesses on V0, G1, V1
       // FP32 Jacobi -> orthogonalised V1, G1 = A V1 -> FP64 Jacobi from (G1, V1): svd_pre.cu
       static bool pre_attr_set[64] = {false};
       if (dev >= 0 && dev < 64 && !pre_attr_set[dev]) {
