@@ -199,6 +199,14 @@ int nd4b_dev_svd_jac1_f64(int device, void* stream, const double* A, double* U, 
 size_t nd4b_dev_qr_workspace(int64_t batch, int rows, int cols);
 size_t nd4b_dev_svd_workspace(int64_t batch, int rows, int cols);
 
+/* NCCL over NVLink, used only to gather results: shard d — counts[d] doubles on the d-th device of the context, e.g.
+ * the outputs of nd4b_dev_*_f64 on that device's contiguous range of the batch — is copied to offset counts[0] + .. + counts[d-1]
+ * of full[e] on EVERY device e (full[e] must hold the sum of the counts; full[d] may contain shards[d] in place).  streams[d]
+ * (cudaStream_t as void*, may be NULL: the library's stream) is the stream of device d the copies are ordered on.  One grouped
+ * ncclBroadcast per shard; NCCL is dlopen()ed on first use (ND4B_NCCL_LIB overrides the library name) and never needed by a
+ * one-device context.  The host-buffer entry points do not use it: their results land in host memory slice by slice. */
+int nd4b_dev_all_gather_f64(const double* const* shards, const int64_t* counts, double* const* full, void* const* streams);
+
 /* Diagnostic for the flop accounting of the benchmark: from now on every SVD launch on `device` adds the sweep count of
  * each matrix to *counter (device uint64, caller-initialised; NULL switches it off).  The Jacobi sweep count is data
  * dependent (C5: 10.06 on average, 12 at most), and work per matrix is proportional to it. */

@@ -17,7 +17,7 @@ SYMBOLS = [
     "nd4b_dev_matmul_f64", "nd4b_dev_cholesky_f64", "nd4b_dev_qr_f64", "nd4b_dev_svd_jac1_f64",
     "nd4b_dev_qr_workspace", "nd4b_dev_svd_workspace", "nd4b_probe_fp64", "nd4b_selfcheck_ieee", "nd4b_tri_solve_f64",
     "nd4b_dev_svd_sweep_counter", "nd4b_dev_svd_pre_sweep_counter", "nd4b_qr_inplace_f64", "nd4b_dev_qr_inplace_f64", "nd4b_matmul_plan_f64", "nd4b_dev_tri_solve_f64", "nd4b_qr_lstsq_f64", "nd4b_dev_qr_lstsq_f64",
-    "nd4b_svd_rank_f64", "nd4b_svd_lstsq_shape", "nd4b_svd_lstsq_f64", "nd4b_dev_svd_lstsq_f64",
+    "nd4b_svd_rank_f64", "nd4b_svd_lstsq_shape", "nd4b_svd_lstsq_f64", "nd4b_dev_svd_lstsq_f64", "nd4b_dev_all_gather_f64",
 ]
 
 OK, E_SINGULAR = 0, 1
@@ -82,6 +82,7 @@ def load():
         "nd4b_dev_qr_inplace_f64": ([C.c_int, vp, dp, dp, dp, dp, i64, C.c_int, C.c_int, C.c_int], C.c_int),
         "nd4b_dev_svd_sweep_counter": ([C.c_int, vp], C.c_int),
         "nd4b_dev_svd_pre_sweep_counter": ([C.c_int, vp], C.c_int),
+        "nd4b_dev_all_gather_f64": ([vp, vp, vp, vp], C.c_int),
         "nd4b_svd_rank_f64": ([dp, ip, i64, C.c_int], C.c_int),
         "nd4b_svd_lstsq_shape": ([ip, C.c_int, ip, C.c_int, ip, C.c_int, ip, C.c_int, ip, C.POINTER(C.c_int)], C.c_int),
         "nd4b_svd_lstsq_f64": ([dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int], C.c_int),

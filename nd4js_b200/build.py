@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(SO, objs):
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, *objs,
-               "-cudart", "static", "-Xlinker", "--no-undefined"]
+               "-cudart", "static", "-Xlinker", "--no-undefined", "-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -3,6 +3,8 @@
 // and the device-resident entry points.  No CPU compute path exists in this library.
 #include "../../include/nd4b.h"
 #include "kernels.h"
+#include <dlfcn.h>
+#include <nccl.h>                 // types and prototypes only: the library is dlopen()ed on the first gather, never linked
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler injects itself
 
 #include <algorithm>
@@ -152,6 +154,7 @@ struct Context {
   std::atomic<uint64_t> calls{0}, launches{0}, h2d{0}, d2h{0}, staged{0};
   int last_sweeps = 0;
   CopyPool* pool = nullptr;   // created on first use of pageable memory
+  std::vector<ncclComm_t> comms;   // one communicator per device of the context (nd4b_dev_all_gather_f64), created on first use
   double t_copy = 0, t_wait = 0, t_alloc = 0;  // seconds spent in staging copies / stream waits / (re)allocation (ND4B_TRACE)
 };
 
@@ -524,6 +527,39 @@ int build_batch_map(const int32_t* a_shape, int a_ndim, const int32_t* b_shape, 
   return ND4B_OK;
 }
 
+// NCCL, loaded at run time for nd4b_dev_all_gather_f64 only
+struct NcclApi {
+  void* handle = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGetVersion) GetVersion = nullptr;
+} g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return ND4B_OK;
+  const char* names[] = {getenv("ND4B_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names)
+    if (n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) return fail(ND4B_E_CUDA, "nd4b: NCCL is not available (%s)", dlerror());
+#define ND4B_NCCL_SYM(field, sym)                                                     \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, #sym));            \
+  if (!g_nccl.field) return fail(ND4B_E_CUDA, "nd4b: %s not found in the NCCL library", #sym)
+  ND4B_NCCL_SYM(CommInitAll, ncclCommInitAll);
+  ND4B_NCCL_SYM(CommDestroy, ncclCommDestroy);
+  ND4B_NCCL_SYM(GroupStart, ncclGroupStart);
+  ND4B_NCCL_SYM(GroupEnd, ncclGroupEnd);
+  ND4B_NCCL_SYM(Broadcast, ncclBroadcast);
+  ND4B_NCCL_SYM(GetErrorString, ncclGetErrorString);
+  ND4B_NCCL_SYM(GetVersion, ncclGetVersion);
+#undef ND4B_NCCL_SYM
+  g_nccl.handle = h;
+  return ND4B_OK;
+}
 }  // namespace
 
 // =================================================================================================
@@ -551,6 +587,7 @@ int nd4b_shutdown(void) {
     if (d.d_info) cudaFree(d.d_info);
     if (d.d_ints) cudaFree(d.d_ints);
   }
+  if (g_nccl.handle) for (auto c : g_ctx->comms) g_nccl.CommDestroy(c);
   delete g_ctx->pool;
   delete g_ctx;
   g_ctx = nullptr;
@@ -1347,6 +1384,53 @@ int nd4b_dev_svd_pre_sweep_counter(int device, unsigned long long* counter) {
   Context* ctx; int sms;
   if (int rc = dev_enter(device, &ctx, &sms)) return rc;
   nd4b::set_svd_pre_sweep_counter(device, counter);
+  return ND4B_OK;
+}
+
+// ---- NCCL gather of device-resident shards ("NCCL over NVLink used only to gather results") ----------------------
+
+#define NC(call)                                                                                          \
+  do {                                                                                                    \
+    ncclResult_t r__ = (call);                                                                            \
+    if (r__ != ncclSuccess) return fail(ND4B_E_CUDA, "NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(r__)); \
+  } while (0)
+
+int nd4b_dev_all_gather_f64(const double* const* shards, const int64_t* counts, double* const* full, void* const* streams) {
+  if (!shards || !counts || !full) return fail(ND4B_E_ARG, "dev_all_gather: null pointer");
+  Context* ctx;
+  if (int rc = get_ctx(&ctx)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const int nd = (int)ctx->devs.size();
+  for (int d = 0; d < nd; d++)
+    if (!shards[d] || !full[d] || counts[d] < 0) return fail(ND4B_E_ARG, "dev_all_gather: bad argument for device %d", d);
+  if (nd == 1) {   // one device: the shard is the whole array
+    CU(cudaSetDevice(ctx->devs[0].id));
+    cudaStream_t st = streams ? (cudaStream_t)streams[0] : ctx->devs[0].slots[0].stream;
+    if (full[0] != shards[0]) CU(cudaMemcpyAsync(full[0], shards[0], (size_t)counts[0] * 8, cudaMemcpyDeviceToDevice, st));
+    return ND4B_OK;
+  }
+  if (int rc = load_nccl()) return rc;
+  if (ctx->comms.empty()) {
+    std::vector<int> ids;
+    for (auto& dv : ctx->devs) ids.push_back(dv.id);
+    ctx->comms.resize(nd);
+    ncclResult_t r = g_nccl.CommInitAll(ctx->comms.data(), nd, ids.data());
+    if (r != ncclSuccess) { ctx->comms.clear(); return fail(ND4B_E_CUDA, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r)); }
+  }
+  // shard r (counts[r] elements on device r) goes to offset sum(counts[0..r)) of every device's full array: one broadcast per
+  // shard inside one group — unequal shards (batch not divisible by the device count) need no padding
+  NC(g_nccl.GroupStart());
+  int64_t off = 0;
+  for (int r = 0; r < nd; r++) {
+    for (int d = 0; d < nd; d++) {
+      cudaStream_t st = streams ? (cudaStream_t)streams[d] : ctx->devs[d].slots[0].stream;
+      ncclResult_t res = g_nccl.Broadcast(d == r ? (const void*)shards[r] : (const void*)(full[d] + off), full[d] + off, (size_t)counts[r],
+                                          ncclDouble, r, ctx->comms[d], st);
+      if (res != ncclSuccess) { g_nccl.GroupEnd(); return fail(ND4B_E_CUDA, "ncclBroadcast failed: %s", g_nccl.GetErrorString(res)); }
+    }
+    off += counts[r];
+  }
+  NC(g_nccl.GroupEnd());
   return ND4B_OK;
 }
 

@@ -211,3 +211,17 @@ def test_dev_matmul_bulk_copy_pipeline(dev, ref):
     assert np.max(np.abs(out.cpu().numpy()[rows] - want) / (np.abs(a[rows]) @ np.abs(b))) <= TOL
     got = out.cpu().numpy()
     assert np.max(np.abs(got - a @ b)) <= 1e-11                    # every tile, against LAPACK-grade numpy
+
+
+def test_dev_all_gather_one_device_context(dev):
+    """nd4b_dev_all_gather_f64 with a one-device context is a device copy (no NCCL needed); the multi-device form is covered by
+    tools/multidev_check.py (tests/test_gpu_multi.py) on boxes with >= 2 GPUs."""
+    t = dev.torch
+    if dev.lib.nd4b_device_count() != 1:
+        pytest.skip("the session's context spans several devices")
+    x = t.arange(1000, dtype=t.float64, device="cuda")
+    y = t.zeros(1000, dtype=t.float64, device="cuda")
+    shards, fulls = (C.c_void_p * 1)(x.data_ptr()), (C.c_void_p * 1)(y.data_ptr())
+    counts, streams = (C.c_int64 * 1)(1000), (C.c_void_p * 1)(dev.stream.value)
+    dev.ok(dev.lib.nd4b_dev_all_gather_f64(shards, counts, fulls, streams))
+    assert (y == x).all()

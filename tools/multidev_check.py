@@ -81,8 +81,54 @@ def main():
         res["equal_bits"][k] = bool(got.shape == one[k].shape and (got.view(np.int64) == one[k].view(np.int64)).all())
     res["cholesky_first_bad_one_device"] = one_bad
     res["cholesky_first_bad_multi_device"] = first_bad(bad)
-    res["all_equal"] = all(res["equal_bits"].values()) and res["cholesky_first_bad_multi_device"] == one_bad and one_bad[1] == 2500
+    res["nccl_gather_equal_bits"] = gather_check(n)
+    res["all_equal"] = (all(res["equal_bits"].values()) and res["cholesky_first_bad_multi_device"] == one_bad and one_bad[1] == 2500
+                        and res["nccl_gather_equal_bits"])
     print(json.dumps(res))
+
+
+def gather_check(n):
+    """nd4b_dev_all_gather_f64: the SVD of a batch sharded over the context's devices through the dev entry points, U / sv / V
+    gathered on every device with NCCL; compared bit for bit with the one-shot host-buffer call."""
+    import ctypes as C
+    import torch
+    L = _lib.load()
+    total = 1000 + 3                                   # not divisible by the device count: unequal shards
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-1, 1, (total, 64, 64))
+    want = [t.numpy() for t in la.svd_jac_1sided(a)]
+    spans = [(total * d // n, total * (d + 1) // n) for d in range(n)]
+    f64 = torch.float64
+    outs, fulls, streams = [], [], []
+    for d, (b0, b1) in enumerate(spans):
+        dev = torch.device("cuda", d)
+        with torch.cuda.device(dev):
+            da = torch.from_numpy(a[b0:b1]).to(dev)
+            cnt = b1 - b0
+            u, sv, v = (torch.empty(cnt, 64, 64, dtype=f64, device=dev), torch.empty(cnt, 64, dtype=f64, device=dev),
+                        torch.empty(cnt, 64, 64, dtype=f64, device=dev))
+            ws = L.nd4b_dev_svd_workspace(cnt, 64, 64)
+            work = torch.empty(ws // 8 + 2, dtype=f64, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            rc = L.nd4b_dev_svd_jac1_f64(d, C.c_void_p(st), C.c_void_p(da.data_ptr()), C.c_void_p(u.data_ptr()), C.c_void_p(sv.data_ptr()),
+                                         C.c_void_p(v.data_ptr()), cnt, 64, 64, None, C.c_void_p(work.data_ptr()), ws)
+            assert rc == 0, _lib.last_error()
+            outs.append((u, sv, v, work, da))
+            fulls.append((torch.empty(total, 64, 64, dtype=f64, device=dev), torch.empty(total, 64, dtype=f64, device=dev),
+                          torch.empty(total, 64, 64, dtype=f64, device=dev)))
+            streams.append(st)
+    ok = True
+    ptrs = lambda seq: (C.c_void_p * n)(*[t.data_ptr() for t in seq])
+    st_arr = (C.c_void_p * n)(*streams)
+    for k, per in enumerate((4096, 64, 4096)):
+        counts = (C.c_int64 * n)(*[(b1 - b0) * per for b0, b1 in spans])
+        rc = L.nd4b_dev_all_gather_f64(ptrs([o[k] for o in outs]), counts, ptrs([f[k] for f in fulls]), st_arr)
+        assert rc == 0, _lib.last_error()
+    for d in range(n):
+        torch.cuda.synchronize(d)
+        for k in range(3):
+            ok = ok and bool((fulls[d][k].cpu().numpy().view(np.int64) == want[k].view(np.int64)).all())
+    return ok
 
 
 if __name__ == "__main__":
