@@ -63,8 +63,10 @@ FP64_PEAK_TFLOPS = 37.15
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the `ncu --set full` captures
 # summarised under profiles/ (file named per entry); None where no capture of the current kernel exists.
 NCU_TRAFFIC_BYTES = {
-    "c2": (1.577e9, "profiles/r01_ncu_c2_final.txt"),
-    "c3": (1.014e9, "profiles/r01_ncu_c3_v3.txt"),
+    "c1": (4.21e6, "profiles/r02_ncu_c1.txt"),    # the operands stay in L2 between launches: the write-back of C is not seen by DRAM
+    "c2": (1.578e9, "profiles/r02_ncu_c2.txt"),
+    "c3": (1.015e9, "profiles/r02_ncu_c3.txt"),
+    "g4k": (1.225e9, "profiles/r02_ncu_g4k_bulk.txt"),
     "c4": (2.849e9, "profiles/r02_ncu_c4_blocked.txt"),
     # three launches per call: FP32 Jacobi 0.774 GB, hand-over 1.824 GB, FP64 Jacobi 2.148 GB (V0, G1, V1 pass through HBM)
     "c5": (4.746e9, "profiles/r02_ncu_c5_pipeline.txt"),
