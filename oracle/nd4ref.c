@@ -292,6 +292,16 @@ int nd4ref_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows
   return ND4REF_OK;
 }
 
+/* qr_decomp_full for any shape (src/la/qr.js:27-77): Q [batch,rows,rows], R [batch,rows,cols]. */
+int nd4ref_qr_full_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
+  if (!A || !Q || !R || batch < 1 || rows < 1 || cols < 1) return ND4REF_E_SHAPE;
+  for (int64_t b = 0; b < batch; b++) {
+    int rc = ref_qr_full_one(rows, cols, A + b * (int64_t)rows * cols, Q + b * (int64_t)rows * rows, R + b * (int64_t)rows * cols);
+    if (rc) return rc;
+  }
+  return ND4REF_OK;
+}
+
 /* -------------------------------------------------------------------- svd ----- */
 
 /* src/la/_svd_jac_utils.js:72-114 */

@@ -54,6 +54,8 @@ int nd4ref_cholesky_f64(const double* S, double* L, int64_t batch, int n, int64_
 /* qr_decomp: src/la/qr.js:80-145 (rows>cols: Givens, thin) and :27-77 (rows<=cols: qr_decomp_full).
  * Q is [batch,rows,min(rows,cols)], R is [batch,min(rows,cols),cols]. */
 int nd4ref_qr_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols);
+/* qr_decomp_full for any shape: src/la/qr.js:27-77.  Q [batch,rows,rows], R [batch,rows,cols]. */
+int nd4ref_qr_full_f64(const double* A, double* Q, double* R, int64_t batch, int rows, int cols);
 
 /* _qr_decomp_inplace: src/la/qr.js:147-183, batched and out of place: R[batch,M,N] <- A rotated to upper trapezoidal form,
  * QtY[batch,M,L] <- the same Givens rotations applied to Y. */

@@ -47,6 +47,8 @@ def lib():
         L.nd4ref_matmul_f64.argtypes = [dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int]
         L.nd4ref_cholesky_f64.argtypes = [dp, dp, i64, C.c_int, C.POINTER(i64)]
         L.nd4ref_qr_f64.argtypes = [dp, dp, dp, i64, C.c_int, C.c_int]
+        L.nd4ref_qr_full_f64.argtypes = [dp, dp, dp, i64, C.c_int, C.c_int]
+        L.nd4ref_qr_full_f64.restype = C.c_int
         L.nd4ref_qr_inplace_f64.argtypes = [dp, dp, dp, dp, i64, C.c_int, C.c_int, C.c_int]
         L.nd4ref_svd_jac2_f64.argtypes = [dp, dp, dp, dp, i64, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.nd4ref_tri_solve_f64.argtypes = [C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, dp, ip, C.c_int]
@@ -127,6 +129,18 @@ def qr_decomp(a):
     q = np.empty(a.shape[:-2] + (rows, l))
     r = np.empty(a.shape[:-2] + (l, cols))
     rc = lib().nd4ref_qr_f64(_dp(a), _dp(q), _dp(r), batch, rows, cols)
+    if rc:
+        raise RefError(rc)
+    return q, r
+
+
+def qr_decomp_full(a):
+    """src/la/qr.js:27-77: complete QR, Q [...,rows,rows], R [...,rows,cols], any shape."""
+    a = _f64(a)
+    rows, cols = a.shape[-2:]
+    q = np.empty(a.shape[:-2] + (rows, rows))
+    r = np.empty(a.shape)
+    rc = lib().nd4ref_qr_full_f64(_dp(a), _dp(q), _dp(r), a.size // (rows * cols), rows, cols)
     if rc:
         raise RefError(rc)
     return q, r
