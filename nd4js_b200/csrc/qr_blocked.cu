@@ -17,6 +17,8 @@
 //   Q = H_1 .. H_32 [I;0] by blocks from the last panel: trailing columns as above with T^T, the panel's own columns
 //       as E_p - V_p (T_p L_p^T) (L_p = unit lower 8x8 head of V_p) — no serial reflector loop in the Q phase.
 // Work per matrix: 40 960 B of HBM traffic, 218 453 flop by the Householder convention.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -46,6 +48,20 @@ constexpr int kMbarOff = kXsOff + 3 * 64;        // mbarrier of the bulk load
 constexpr int kQbWarpDoubles = kMbarOff + 16;    // 2128 doubles = 17 024 B (a multiple of 128 B)
 // The first 2048 doubles double as the landing zone of the bulk load of A (TMA, 16 KiB) and as the staging tile of the
 // bulk store of Q: 8-byte per-lane global accesses in the fragment layout cost 4 L1 tag look-ups per instruction.
+
+// Tensor-map variant (IO == 2): A arrives as two TMA tile loads (UTMALDG, box 16 columns x 64 rows, SWIZZLE_128B) and Q leaves
+// as two tile stores (UTMASTG).  A row of a box is one 128-byte line whose 16-byte chunks are xor-ed with (row & 7), which is
+// exactly what makes the transposing fragment accesses conflict-free: the sixteen lanes (g < 4, t) of a half-warp touch rows
+// 2t+e — chunk (g >> 1) ^ (2t + e) takes eight different values — so every 8-byte access is 2 wavefronts instead of 8
+// (profiles/r02_ncu_c4_blocked.txt: 1 440 of the 3 150 shared-memory wavefronts per matrix were these loads and stores).
+// The swizzle needs 1 KiB-aligned boxes: the per-warp region is rounded up to 17 KiB.
+constexpr int kQbWarpDoublesT = 2176;            // 17 408 B
+__device__ __forceinline__ int tm_idx(int i, int j, int g, int t, int e) {   // element (row 8j+2t+e, column 8i+g) in the swizzled landing zone
+  return (i >> 1) * 1024 + (8 * j + 2 * t + e) * 16 + ((((4 * (i & 1)) + (g >> 1)) ^ (2 * t + e)) << 1) + (g & 1);
+}
+// V panels in shared memory: row-major rows of 8, the column pairs of a row xor-ed with ((row >> 1) & 3): the 16-byte row reads
+// stay conflict-free and the transposing 8-byte stores (lane (g,t) -> row 2t+e, column g) drop from 8 wavefronts to 4.
+__device__ __forceinline__ int v_sw(int row) { return ((row >> 1) & 3) << 1; }
 
 struct Acc { double x, y; };  // 8x8 tile in accumulator layout: x = M[g][2t], y = M[g][2t+1]
 
@@ -97,6 +113,17 @@ __device__ __forceinline__ void bulk_store(void* dst, const void* src, unsigned 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// One lane: TMA tile load of the box at (x = column, y = row) of a 2-D tensor map into shared memory (UTMALDG), completion
+// on an mbarrier that already expects the bytes; tile store shared -> global (UTMASTG).
+__device__ __forceinline__ void tmap_load_2d(void* dst, const CUtensorMap* tm, int x, int y, void* mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(x), "r"(y), "r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void tmap_store_2d(const CUtensorMap* tm, int x, int y, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<unsigned long long>(tm)), "r"(x), "r"(y), "r"(smem_u32(src)) : "memory");
 }
 
 // Predicated 16-byte shared store: lanes with pred == false issue nothing (no divergence, no wavefronts).
@@ -261,7 +288,7 @@ __device__ __forceinline__ void qb_trailing(double (&a)[4][8][2], const double* 
     Z.y = -Z.y;
 #pragma unroll
     for (int j = P; j < 8; j++) {
-      const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + 2 * t);
+      const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + ((2 * t) ^ v_sw(g)));
       dmma884(a[i][j][0], a[i][j][1], Z.x, v.x);
       dmma884(a[i][j][0], a[i][j][1], Z.y, v.y);
     }
@@ -305,8 +332,8 @@ __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, dou
   a[P][P][1] = (2 * t + 1 > g) ? a[P][P][1] : ((2 * t + 1 == g) ? 1.0 : 0.0);
 #pragma unroll
   for (int j = P; j < 8; j++) {
-    vs[v_off(P) + (8 * (j - P) + 2 * t) * 8 + g] = a[P][j][0];
-    vs[v_off(P) + (8 * (j - P) + 2 * t + 1) * 8 + g] = a[P][j][1];
+    vs[v_off(P) + (8 * (j - P) + 2 * t) * 8 + (g ^ (2 * t))] = a[P][j][0];      // v_sw(row 2t+e) = 2t
+    vs[v_off(P) + (8 * (j - P) + 2 * t + 1) * 8 + (g ^ (2 * t))] = a[P][j][1];
   }
   QB_MARK(3);
   Acc T, TT;
@@ -331,7 +358,7 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
   // columns right of the panel: nonzero from row 8(P+1) on, filled from row 8P on by this update
   if (P < 3) qb_trailing<P, P + 1>(a, vs, g, t, T);
   // the panel's own columns: E_P - V_P (T_P L_P^T)
-  const double2 l = *reinterpret_cast<const double2*>(vs + v_off(P) + g * 8 + 2 * t);
+  const double2 l = *reinterpret_cast<const double2*>(vs + v_off(P) + g * 8 + ((2 * t) ^ v_sw(g)));
   Acc M = mm8(Acc{l.x, l.y}, T);  // (L_P T_P^T)[b][c] = M^T
   M.x = -M.x;
   M.y = -M.y;
@@ -339,7 +366,7 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
   for (int j = 0; j < P; j++) { a[P][j][0] = 0.0; a[P][j][1] = 0.0; }
 #pragma unroll
   for (int j = P; j < 8; j++) {
-    const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + 2 * t);
+    const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + ((2 * t) ^ v_sw(g)));
     double q0 = (j == P && g == 2 * t) ? 1.0 : 0.0, q1 = (j == P && g == 2 * t + 1) ? 1.0 : 0.0;
     dmma884(q0, q1, M.x, v.x);
     dmma884(q0, q1, M.y, v.y);
@@ -351,16 +378,22 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
 // PADDED: any rows <= 64, cols <= 32: the matrix is zero-padded into the 64 x 32 register tile on load (zero rows leave the
 // reflectors unchanged, zero columns give identity reflectors after the last real column), and only the rows x L block
 // of Q and the L x cols block of R are stored.
-template <int WARPS, int MINB, bool REREAD, bool PADDED>
+template <int WARPS, int MINB, bool REREAD, bool PADDED, bool TMAP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch,
-                       int rows, int cols) {
+                       int rows, int cols, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_q) {
   extern __shared__ __align__(16) double qb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int64_t m = (int64_t)blockIdx.x * WARPS + warp;
   if (m >= batch) return;  // warp-uniform; the kernel has no block-level barriers
-  double* vs = qb_smem + warp * kQbWarpDoubles;
+  double* vs;
+  if (TMAP) {  // 1 KiB-aligned warp regions (SWIZZLE_128B); the launch adds 1 KiB of slack
+    const unsigned base = smem_u32(qb_smem), pad = (1024u - (base & 1023u)) & 1023u;
+    vs = reinterpret_cast<double*>(reinterpret_cast<char*>(qb_smem) + pad) + warp * kQbWarpDoublesT;
+  } else {
+    vs = qb_smem + warp * kQbWarpDoubles;
+  }
   double* ts = vs + kVDoubles;
   const int L = PADDED ? (rows < cols ? rows : cols) : 32;
   const double* a_in = A + m * (PADDED ? rows * cols : 2048);
@@ -368,8 +401,26 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   long long qb_tm = clock64();
   (void)qb_tm;
   double a[4][8][2];
-  const bool bulk = !PADDED && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;  // kernel-uniform
-  if (bulk) {
+  const bool bulk = !TMAP && !PADDED && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;  // kernel-uniform
+  if (TMAP) {
+    if (lane == 0) {
+      const unsigned mb = smem_u32(vs + kMbarOff);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(16384u) : "memory");
+      tmap_load_2d(vs, &tm_a, 0, (int)(64 * m), vs + kMbarOff);
+      tmap_load_2d(vs + 1024, &tm_a, 16, (int)(64 * m), vs + kMbarOff);
+    }
+    __syncwarp();
+    bulk_load_wait(vs + kMbarOff);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i][j][e] = vs[tm_idx(i, j, g, t, e)];
+    __syncwarp();  // the landing zone becomes the V store
+  } else if (bulk) {
     if (lane == 0) bulk_load_start(vs, a_in, 16384, vs + kMbarOff);
     __syncwarp();
     bulk_load_wait(vs + kMbarOff);
@@ -435,7 +486,23 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   QB_MARK(6);
 
   double* q_out = Q + m * (PADDED ? rows * L : 2048);
-  if (bulk) {
+  if (TMAP) {
+    __syncwarp();  // every lane is done with the V store
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) vs[tm_idx(i, j, g, t, e)] = flip(a[i][j][e], sgn[i]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tmap_store_2d(&tm_q, 0, (int)(64 * m), vs);
+      tmap_store_2d(&tm_q, 16, (int)(64 * m), vs + 1024);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else if (bulk) {
     __syncwarp();  // every lane is done with the V store
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -489,7 +556,7 @@ __device__ __forceinline__ void qb_apply_y(double (&yb)[8][2], const double (&a)
   Z.y = -Z.y;
 #pragma unroll
   for (int j = P; j < 8; j++) {
-    const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + 2 * t);
+    const double2 v = *reinterpret_cast<const double2*>(vs + v_off(P) + (8 * (j - P) + g) * 8 + ((2 * t) ^ v_sw(g)));
     dmma884(yb[j][0], yb[j][1], Z.x, v.x);
     dmma884(yb[j][0], yb[j][1], Z.y, v.y);
   }
@@ -578,18 +645,45 @@ qr64x32_inplace_kernel(const double* __restrict__ A, const double* __restrict__ 
 
 }  // namespace
 
-template <int WARPS, int MINB, bool REREAD, bool PADDED>
-static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols) {
+// 2-D tensor map over a batch of 64 x 32 matrices seen as one [batch*64, 32] row-major array: box = 16 columns x 64 rows
+// (one 128-byte line per row), SWIZZLE_128B.  The encoder comes from the driver through the runtime (no libcuda link).
+static bool qb_encode_map(CUtensorMap* tm, const void* base, int64_t batch) {
+  typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode enc = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<Encode>(fn);
+    else
+      (void)cudaGetLastError();
+  }
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {32, (cuuint64_t)batch * 64};
+  const cuuint64_t strides[1] = {256};
+  const cuuint32_t box[2] = {16, 64}, estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int WARPS, int MINB, bool REREAD, bool PADDED, bool TMAP = false>
+static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols,
+                             const CUtensorMap* tm_a = nullptr, const CUtensorMap* tm_q = nullptr) {
   static bool attr_set[64] = {false};
-  constexpr size_t smem = sizeof(double) * kQbWarpDoubles * WARPS;
+  constexpr size_t smem = TMAP ? sizeof(double) * kQbWarpDoublesT * WARPS + 1024 : sizeof(double) * kQbWarpDoubles * WARPS;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED, TMAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(A, Q, R, batch, rows, cols);
+  static const CUtensorMap none{};
+  qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED, TMAP><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(
+      A, Q, R, batch, rows, cols, tm_a ? *tm_a : none, tm_q ? *tm_q : none);
   return cudaGetLastError();
 }
 
@@ -599,6 +693,14 @@ static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double*
 // the panel chains of the locked warps then collide on the shared-memory pipe instead.
 cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int variant) {
   if (variant == 2) return qb_launch<4, 2, false, false>(s, A, Q, R, batch, 64, 32);
+  // default: TMA tile loads / stores through swizzled tensor maps (ND4B_QR_TMAP=0: the linear bulk copies of round 1)
+  static const bool want_tmap = [] { const char* e = getenv("ND4B_QR_TMAP"); return !(e && e[0] == '0'); }();
+  const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;
+  if (want_tmap && aligned && batch * 64 < 0x7fffffffLL) {
+    CUtensorMap tm_a, tm_q;
+    if (qb_encode_map(&tm_a, A, batch) && qb_encode_map(&tm_q, Q, batch))
+      return qb_launch<4, 3, true, false, true>(s, A, Q, R, batch, 64, 32, &tm_a, &tm_q);
+  }
   return qb_launch<4, 3, true, false>(s, A, Q, R, batch, 64, 32);
 }
 

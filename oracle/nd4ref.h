@@ -8,16 +8,16 @@
  * contraction: build with -ffp-contract=off) of one nd4js v1.3.0 routine; the cited
  * file:line ranges are relative to the reference checkout.
  *
- * Pinning status: the reference ships NO stored numeric vectors for these
- * four routines and no JS engine exists in this image, so value-level parity is pinned by
- * this restatement only.  What the reference's own tests DO pin, and tests/ checks against
- * this oracle:  matmul known answers (src/la/matmul_test.js:32-78), the cholesky docstring
- * example (src/help.js:1876-1885), exactness of svd_jac* on diagonal input
- * (src/la/_generic_test_svd_decomp.js:180-216) and the property suites with the
- * reference's tolerances (qr_test.js:169-187, cholesky_test.js:72-123,
- * _generic_test_svd_decomp.js:79-163).  nd.la.svd_jac_1sided does not exist in the
- * reference snapshot: for it PARITY IS UNPINNED by the reference; the oracle's
- * svd_jac_2sided restatement supplies the singular values it is compared with.
+ * Pinning status: PINNED BY THE REFERENCE ITSELF.  The reference's own JavaScript (src/la/*.js of
+ * nd4js v1.3.0) runs in the build container inside QJSEngine (Qt 6.6.3, shipped with Nsight Compute; oracle/jsref/qjs.py);
+ * oracle/jsref/gen_golden.py commits its outputs on 81 seeded cases as tests/golden/jsref_golden.npz, and
+ * tests/test_jsref_golden.py checks that every function below reproduces them BIT FOR BIT (matmul2, matmul chains,
+ * cholesky_decomp incl. the failure texts, tril/triu/cholesky_solve, qr_decomp, qr_decomp_full, _qr_decomp_inplace,
+ * qr_lstsq, svd_jac_2sided, svd_rank, svd_lstsq, svd_solve); tests/test_jsref_live.py repeats it on fresh seeds against
+ * the live engine.  The reference's own known answers are checked as well (matmul_test.js:32-78, help.js:1876-1885,
+ * _generic_test_svd_decomp.js:180-216) and its property suites with its tolerances.
+ * nd.la.svd_jac_1sided does not exist in the reference snapshot: for it PARITY IS UNPINNED by the reference; the
+ * reference-pinned svd_jac_2sided supplies the singular values it is compared with.
  */
 #ifndef ND4REF_H
 #define ND4REF_H
