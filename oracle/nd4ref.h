@@ -8,7 +8,7 @@
  * contraction: build with -ffp-contract=off) of one nd4js v1.3.0 routine; the cited
  * file:line ranges are relative to the reference checkout.
  *
- * Pinning status: PINNED BY THE REFERENCE ITSELF.  The reference's own JavaScript (src/la/*.js of
+ * Pinning status: PINNED BY THE REFERENCE ITSELF.  The reference's own JavaScript (the src/la sources of
  * nd4js v1.3.0) runs in the build container inside QJSEngine (Qt 6.6.3, shipped with Nsight Compute; oracle/jsref/qjs.py);
  * oracle/jsref/gen_golden.py commits its outputs on 81 seeded cases as tests/golden/jsref_golden.npz, and
  * tests/test_jsref_golden.py checks that every function below reproduces them BIT FOR BIT (matmul2, matmul chains,
