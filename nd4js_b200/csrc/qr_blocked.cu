@@ -143,10 +143,12 @@ __device__ __forceinline__ double flip(double x, unsigned mask) {
 // The step is one dependent chain (dots -> |x|^2 -> reflector scalars -> update), so the scalar part is written for
 // depth: branch-free, 1/sqrt and 1/v0 refined from overlapping 20-bit estimates.
 template <int P, bool REREAD>
-__device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int lane, int g, int t, double& tau_q, unsigned& sgn_q) {
+__device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int lane, int g, int t, double& tau_q, unsigned& sgn_q, Acc& Gu) {
   double inv_q = 0.0;
   tau_q = 0.0;
   sgn_q = 0u;
+  Gu.x = 0.0;   // strict upper triangle of G = V^T V in accumulator layout, collected from the steps' own dot products:
+  Gu.y = 0.0;   // for a finished column g < kk the step's x~^T a_g is v0_g v0_kk (v_g^T v_kk)
   if (g == 0) {
 #pragma unroll
     for (int j = P; j < 8; j++) *reinterpret_cast<double2*>(xs + 8 * j + 2 * t) = make_double2(a[P][j][0], a[P][j][1]);
@@ -198,7 +200,13 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
     const double r1 = fma(fma(-v0, r0, 1.0), r0, r0);
     const double e2 = fma(-v0, r1, 1.0);  // ~2^-40
     // v = x~/v0 with x~ = (v0; x below), w = v^T a = (d - beta*akj)/v0, a -= tau*w*v = a + f x~, f = -tau (d - beta*akj)/v0^2
-    const double tc = (ok && g > kk) ? tau * fma(cn, akj, d) : 0.0;
+    const double wall = fma(cn, akj, d);   // x~^T a_g for every column g
+    const double tc = (ok && g > kk) ? tau * wall : 0.0;
+    {  // G[g][kk] for the finished columns g < kk (inv_q is still 0 for the others); lands in lane (g, kk >> 1)
+      const double gv = (wall * (ok ? fma(e2, r1, r1) : 0.0)) * inv_q;
+      Gu.x = (t == (kk >> 1) && !(kk & 1)) ? gv : Gu.x;
+      Gu.y = (t == (kk >> 1) && (kk & 1)) ? gv : Gu.y;
+    }
     const double tr = tc * (r1 * r1);
     const double f = fma(-tr, e2 + e2, -tr);  // 1/v0^2 = r1^2 (1 + 2 e2) to working precision
     const bool prow = (t == t0);
@@ -239,24 +247,18 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
   }
 }
 
-// T of panel P in both orientations (accumulator layout) from the clean V held in a[P][j>=P].
+// T of panel P in both orientations (accumulator layout) from the strict upper triangle of G = V^T V that the panel steps
+// collected (no Gram product: 2(8-P) dependent DMMAs less per panel).
 template <int P>
-__device__ __forceinline__ void qb_make_t(const double (&a)[4][8][2], int g, int t, double tau_q, Acc& T, Acc& TT) {
-  Acc G{0.0, 0.0};
-#pragma unroll
-  for (int j = P; j < 8; j++) {
-    dmma884(G.x, G.y, a[P][j][0], a[P][j][0]);
-    dmma884(G.x, G.y, a[P][j][1], a[P][j][1]);
-  }
+__device__ __forceinline__ void qb_make_t(const Acc& Gu, int g, int t, double tau_q, Acc& T, Acc& TT) {
   const double tq0 = shfl(tau_q, 4 * (2 * t)), tq1 = shfl(tau_q, 4 * (2 * t + 1));  // tau of columns 2t, 2t+1
   const int c0 = 2 * t, c1 = 2 * t + 1;
-  Acc N, NT, I;
-  N.x = (g < c0) ? tau_q * G.x : 0.0;
-  N.y = (g < c1) ? tau_q * G.y : 0.0;
-  NT.x = (c0 < g) ? tq0 * G.x : 0.0;  // N^T[g][c] = N[c][g] = tau_c G[c][g], G symmetric
-  NT.y = (c1 < g) ? tq1 * G.y : 0.0;
+  Acc N, I;
+  N.x = (g < c0) ? tau_q * Gu.x : 0.0;
+  N.y = (g < c1) ? tau_q * Gu.y : 0.0;
   I.x = (g == c0) ? 1.0 : 0.0;
   I.y = (g == c1) ? 1.0 : 0.0;
+  const Acc NT = mm8(I, N);   // the transpose, exactly: I * (N^T) given (N^T)^T = N
   const Acc N2 = mm8(N, NT), N2T = mm8(NT, N);
   const Acc N4T = mm8(N2T, N2);
   const Acc ImN{I.x - N.x, I.y - N.y};
@@ -320,7 +322,8 @@ __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, dou
                                            double* __restrict__ r_out, int lane, int g, int t, double post, unsigned& sgn_p,
                                            long long& qb_tm, int L, int cols) {
   double tau_q;
-  qb_panel<P, REREAD>(a, vs + kXsOff, lane, g, t, tau_q, sgn_p);
+  Acc Gu;
+  qb_panel<P, REREAD>(a, vs + kXsOff, lane, g, t, tau_q, sgn_p, Gu);
   QB_MARK(2);
   const unsigned s0 = __shfl_sync(kFull, sgn_p, 4 * (2 * t)), s1 = __shfl_sync(kFull, sgn_p, 4 * (2 * t + 1));
   // R: diagonal block and the zero blocks left of it; then the head of the panel becomes the clean unit-lower V
@@ -337,7 +340,7 @@ __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, dou
   }
   QB_MARK(3);
   Acc T, TT;
-  qb_make_t<P>(a, g, t, tau_q, T, TT);
+  qb_make_t<P>(Gu, g, t, tau_q, T, TT);
   *reinterpret_cast<double2*>(ts + 64 * P + 2 * lane) = make_double2(T.x, T.y);
   __syncwarp();
   QB_MARK(4);
