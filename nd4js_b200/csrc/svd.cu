@@ -543,7 +543,7 @@ __device__ __forceinline__ void cb_step(CbState& st, double2* wcs, int warp, int
   }
   // (alpha, beta) of the 8 pairs to every lane: group leaders publish to a warp-private smem line, uniform 16-byte reads
   __syncwarp();
-  if ((lane & 3) == 0) wcs[grp] = make_double2(r.alpha, r.beta);
+  if ((lane & 2) == 0) reinterpret_cast<double*>(wcs)[2 * grp + (lane & 1)] = (lane & 1) ? r.beta : r.alpha;   // 2 wavefronts (a 16-byte store from 8 scattered lanes takes 4)
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; j++) {

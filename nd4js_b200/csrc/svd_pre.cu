@@ -211,7 +211,7 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
           rem.di = __shfl_xor_sync(kFull, back.di, 4 * msk);
           if (lower) cb = rem; else ca = rem;
           __syncwarp();
-          if ((lane & 3) == 0) wcs[grp] = mult;
+          reinterpret_cast<float*>(wcs)[lane] = (lane & 2) ? mult.z : mult.x;   // (-alpha, -alpha, beta, beta) of group grp: one 128-byte wavefront
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -235,7 +235,7 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
         cb.d = __shfl_sync(kFull, cb.d, next_grp_lane);
         cb.di = __shfl_sync(kFull, cb.di, next_grp_lane);
         __syncwarp();
-        if ((lane & 3) == 0) wcs[grp] = mult;
+        reinterpret_cast<float*>(wcs)[lane] = (lane & 2) ? mult.z : mult.x;   // (-alpha, -alpha, beta, beta) of group grp: one 128-byte wavefront
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -308,11 +308,13 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
 // ------------------------------------------------------------------------------------------------
 // V1 = V0 (I + E)^(-1/2),  G1 = A V1  — FP64 on the DMMA pipe, operands in shared memory.
 // 8 warps per matrix; warp w owns the 8 output rows 8w..8w+7 (eight 8x8 tiles), lane = 4g + t holds C[g][2t], C[g][2t+1]
-// of every tile.  Row strides: 72 doubles for matrices read as the B operand (element [k0+t][n0+g]: conflict-free when the
-// stride is 8 mod 16), 68 for A = the A operand of the last product (element [i0+g][k0+t]: 4 mod 16).  E is symmetric, so
-// wherever E is the A operand it is read through its transpose with the conflict-free pattern.
+// of every tile.  Row stride 68 doubles (4 mod 16) for every operand: an 8-byte fragment load is served half a warp at a time
+// (lanes g < 4, t), and both the B pattern [k0+t][n0+g] and the A pattern [i0+g][k0+t] then touch the sixteen double-wide banks
+// 4t + g / 4g + t once each.  (Round 2 first used 72 for the B operands — 8 mod 16 puts t and t+2 on the same banks:
+// 11 264 of the 22 528 fragment-load wavefronts per matrix were conflicts and the kernel ran at 89 % of the LSU pipe,
+// profiles/r02_ncu_c5_pipeline.txt.)  E is symmetric, so wherever E is the A operand it is read through its transpose.
 // ------------------------------------------------------------------------------------------------
-constexpr int kOrthoLD = 72, kOrthoLDA = 68;
+constexpr int kOrthoLD = 68, kOrthoLDA = 68;
 constexpr size_t kOrthoSmem = sizeof(double) * (3 * 64 * kOrthoLD + 16);
 
 template <class FA, class FB>
