@@ -279,9 +279,13 @@ __device__ __forceinline__ void qb_trailing(double (&a)[4][8][2], const double* 
   for (int i = P + 1; i < 4; i++) {
     Acc W{0.0, 0.0}, W2{0.0, 0.0};
 #pragma unroll
-    for (int j = J0; j < 8; j++) {  // two independent accumulation chains
+    for (int j = J0; j < 8; j++) {  // two independent accumulation chains (-DQB_SINGLE_W: one, for A/B timing of the pipe contention)
       dmma884(W.x, W.y, a[i][j][0], a[P][j][0]);
+#ifdef QB_SINGLE_W
+      dmma884(W.x, W.y, a[i][j][1], a[P][j][1]);
+#else
       dmma884(W2.x, W2.y, a[i][j][1], a[P][j][1]);
+#endif
     }
     W.x += W2.x;
     W.y += W2.y;

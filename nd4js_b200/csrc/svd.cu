@@ -145,6 +145,15 @@ constexpr size_t kSvd64Smem = sizeof(double) * (2 * 64 * kSvd64LD + 64) + sizeof
 // (zero columns completed to an orthonormal basis) and writes U, sv, V.  Called by all 256 threads after a barrier.
 // PADDED: the matrix is rows x cols (both <= 64) inside the zero-padded 64 x 64 tile; only the L = min(rows, cols) leading
 // singular triplets are written (U rows x L, sv L, V L x cols), and only zero columns among those are completed.
+// Does column k (norm sk) come before column j (norm sj) in the output order?  Descending, stable, and TOTAL: a NaN norm
+// ranks before every number (ties among NaNs by index), so that the ranks are a permutation whatever the input — with the
+// plain comparisons a NaN column shares rank 0 with the largest one and a slot of perm[] is never written.
+__device__ __forceinline__ bool sv_before(double sk, int k, double sj, int j) {
+  const bool nk = sk != sk, nj = sj != sj;
+  if (nk || nj) return nk && (!nj || k < j);
+  return (sk > sj) || (sk == sj && k < j);
+}
+
 template <int T, bool PADDED = false>
 __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* sq, int* perm, int* zero_flag, int* done_flag,
                                                double* __restrict__ U, double* __restrict__ SV, double* __restrict__ V, int64_t m,
@@ -186,7 +195,7 @@ __device__ __forceinline__ void svd64_epilogue(double* Gs, double* Vs, double* s
     for (int k = 0; k < N; k++) {
       const double sk = sq[k];
       const bool pk = PADDED && zero_flag[k];
-      if (!pk) rank += (sk > sj) || (sk == sj && k < tid);
+      if (!pk) rank += sv_before(sk, k, sj, tid);
       else pads_before += (k < tid);
       smax = fmax(smax, sk);
     }
@@ -857,7 +866,7 @@ svd_generic_kernel(const double* __restrict__ A, double* __restrict__ U, double*
     double smax = 0.0;
     for (int k = 0; k < n; k++) {
       const double sk = sig[k];
-      rank += (sk > sj) || (sk == sj && k < j);
+      rank += sv_before(sk, k, sj, j);
       smax = fmax(smax, sk);
     }
     perm[rank] = j;
@@ -985,7 +994,7 @@ svd_tiny_kernel(const double* __restrict__ A, double* __restrict__ U, double* __
     unsigned zero_mask = 0, done_mask = 0;
     for (int j = 0; j < n; j++) {
       int rank = 0;
-      for (int k = 0; k < n; k++) rank += (sig[k] > sig[j]) || (sig[k] == sig[j] && k < j);
+      for (int k = 0; k < n; k++) rank += sv_before(sig[k], k, sig[j], j);
       permd[rank] = (double)j;
       if (sig[j] < smax * kZeroRel || sig[j] < DBL_MIN) zero_mask |= 1u << j;
     }
