@@ -183,32 +183,37 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
     const double s = shfl(d, 4 * kk);
     const int e0 = kk & 1, t0 = kk >> 1;
     const double akj = shfl(e0 ? a[P][P][1] : a[P][P][0], (lane & ~3) | t0);  // my column's element in the pivot row
-    const bool ok = s > 0x1p-900;  // else a (numerically) zero column: H = I
+    // 2^-900 < s < inf (else a numerically zero column, H = I; NaN: H = I as well) — on the integer pipe: every FP64 instruction
+    // of this chain queues behind the DMMA streams of the neighbouring warps (math-pipe throttle is 45 % of the panel's stalls)
+    const bool ok = (unsigned)(__double2hiint(s) - 0x07B00001) < (unsigned)(0x7ff00000 - 0x07B00001);
     const double ss = ok ? s : 1.0;
-    // nrm = sqrt(ss), rn = 1/nrm by one cubic step from the 20-bit estimate y0; 1/v0 by Newton from an estimate taken at
-    // the approximate v0 (the two special-function latencies overlap)
+    // nrm = sqrt(ss), rn = 1/nrm by one cubic step from the 20-bit estimate y0.  The update needs tau / v0^2, and with
+    // |v0| = |x0| + nrm, tau = |v0| / nrm that is 1 / q, q = nrm |v0| = ss + |x0| nrm: one reciprocal, estimated early from the
+    // approximate norm (the two special-function latencies overlap) and corrected to ~2^-57 by a second-order step at the exact q.
+    const double ax0 = fabs(x0);
     const double y0 = rsqrt_approx(ss);
     const double sy = ss * y0;
-    const double r0 = rcp_approx(x0 + copysign(sy, x0));
+    const double rq0 = rcp_approx(fma(ax0, sy, ss));
     const double e = fma(-sy, y0, 1.0);
     const double pe = fma(0.375, e, 0.5);
     const double nrm = fma(sy * e, pe, sy);
     const double rn = fma(y0 * e, pe, y0);
     const double cn = copysign(nrm, x0);  // -beta
     const double v0 = x0 + cn;
-    const double tau = fma(fabs(x0), rn, 1.0);
-    const double r1 = fma(fma(-v0, r0, 1.0), r0, r0);
-    const double e2 = fma(-v0, r1, 1.0);  // ~2^-40
-    // v = x~/v0 with x~ = (v0; x below), w = v^T a = (d - beta*akj)/v0, a -= tau*w*v = a + f x~, f = -tau (d - beta*akj)/v0^2
+    const double tau = fma(ax0, rn, 1.0);
+    const double q = fma(ax0, nrm, ss);
+    const double eq = fma(-q, rq0, 1.0);                 // ~2^-19
+    const double rq = fma(rq0, fma(eq, eq, eq), rq0);    // 1 / q
+    // v = x~/v0 with x~ = (v0; x below): a -= tau (v^T a) v = a + f x~,  f = -(x~^T a) / q,  x~^T a = d - beta*akj
     const double wall = fma(cn, akj, d);   // x~^T a_g for every column g
-    const double tc = (ok && g > kk) ? tau * wall : 0.0;
+    const double wsel = (ok && g > kk) ? wall : 0.0;
+    const double f = -(wsel * rq);
+    const double inv_v0 = ok ? copysign(nrm * rq, x0) : 0.0;   // 1 / v0 = nrm / q, sign of x0
     {  // G[g][kk] for the finished columns g < kk (inv_q is still 0 for the others); lands in lane (g, kk >> 1)
-      const double gv = (wall * (ok ? fma(e2, r1, r1) : 0.0)) * inv_q;
+      const double gv = (wall * inv_v0) * inv_q;
       Gu.x = (t == (kk >> 1) && !(kk & 1)) ? gv : Gu.x;
       Gu.y = (t == (kk >> 1) && (kk & 1)) ? gv : Gu.y;
     }
-    const double tr = tc * (r1 * r1);
-    const double f = fma(-tr, e2 + e2, -tr);  // 1/v0^2 = r1^2 (1 + 2 e2) to working precision
     const bool prow = (t == t0);
 #pragma unroll
     for (int j = P; j < 8; j++) {
@@ -230,7 +235,7 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
     {  // the pivot quad records its reflector (selects, no divergence)
       const bool piv = (g == kk);
       tau_q = piv ? (ok ? tau : 0.0) : tau_q;
-      inv_q = piv ? (ok ? fma(e2, r1, r1) : 0.0) : inv_q;
+      inv_q = piv ? inv_v0 : inv_q;
       sgn_q = piv ? ((ok ? ~(unsigned)__double2hiint(cn) : 0u) & 0x80000000u) : sgn_q;  // beta = -cn < 0: flip the row of R / column of Q
       const double beta = ok ? -cn : 0.0;
       a[P][P][0] = (piv && prow && !e0) ? beta : a[P][P][0];
