@@ -165,22 +165,38 @@ __device__ __forceinline__ void qb_panel(double (&a)[4][8][2], double* xs, int l
     __syncwarp();
     const double x0 = xb[8 * P + kk];  // pivot element
     double x[8][2];
+#ifdef QB_DOT8
+    // eight independent chains while the panel is tall (P < 2: 16 / 14 products): depth 2 + 3 adds instead of 4 + 2
+    constexpr bool kDot8 = P < 2;
+#else
+    constexpr bool kDot8 = false;
+#endif
     double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;  // four independent chains
+    double d02 = 0.0, d03 = 0.0, d12 = 0.0, d13 = 0.0;
 #pragma unroll
     for (int j = P; j < 8; j++) {
       const double2 v = *reinterpret_cast<const double2*>(xb + 8 * j + 2 * t);
       x[j][0] = v.x;
       x[j][1] = v.y;
-      if ((j - P) & 1) { d01 = fma(v.x, a[P][j][0], d01); d11 = fma(v.y, a[P][j][1], d11); }
-      else { d00 = fma(v.x, a[P][j][0], d00); d10 = fma(v.y, a[P][j][1], d10); }
+      const int c = (j - P) & (kDot8 ? 3 : 1);
+      if (c == 0) { d00 = fma(v.x, a[P][j][0], d00); d10 = fma(v.y, a[P][j][1], d10); }
+      else if (c == 1) { d01 = fma(v.x, a[P][j][0], d01); d11 = fma(v.y, a[P][j][1], d11); }
+      else if (c == 2) { d02 = fma(v.x, a[P][j][0], d02); d12 = fma(v.y, a[P][j][1], d12); }
+      else { d03 = fma(v.x, a[P][j][0], d03); d13 = fma(v.y, a[P][j][1], d13); }
     }
-    double d = (d00 + d01) + (d10 + d11);
-    // quad totals, then |x|^2 (rows >= k) from the pivot quad.  (Fetching the pivot quad's four partial sums in parallel
-    // shortens the chain by two shuffle latencies but costs six more SHFL: the panel phase is bound by the shared-memory /
-    // shuffle pipe of the SM — 12 warps, ~90 pipe cycles per step each — not by the length of the chain.)
+    double d = kDot8 ? ((d00 + d01) + (d02 + d03)) + ((d10 + d11) + (d12 + d13)) : (d00 + d01) + (d10 + d11);
+    // quad totals, and |x|^2 (rows >= k) = the pivot quad's total.  The pivot quad's two half sums are fetched while the own
+    // quad finishes its butterfly: one shuffle latency off the chain for one more SHFL (since the transposing accesses of the
+    // load / store phases are conflict-free, the shared-memory pipe has the room).
+#ifdef QB_S_LATE
     d += shfl_xor(d, 1);
     d += shfl_xor(d, 2);
     const double s = shfl(d, 4 * kk);
+#else
+    d += shfl_xor(d, 1);
+    const double s = shfl(d, 4 * kk) + shfl(d, 4 * kk + 2);
+    d += shfl_xor(d, 2);
+#endif
     const int e0 = kk & 1, t0 = kk >> 1;
     const double akj = shfl(e0 ? a[P][P][1] : a[P][P][0], (lane & ~3) | t0);  // my column's element in the pivot row
     // 2^-900 < s < inf (else a numerically zero column, H = I; NaN: H = I as well) — on the integer pipe: every FP64 instruction
