@@ -1,5 +1,6 @@
 """Static SASS opcode histogram of the hot kernels in nd4js_b200/libnd4b.so (cuobjdump, no GPU needed): the evidence for which
-hardware paths a kernel uses — DMMA (FP64 tensor pipe), FFMA2 / FMUL2 (packed FP32), UBLKCP (TMA bulk copies), LDGSTS (cp.async).
+hardware paths a kernel uses — DMMA (FP64 tensor pipe), FFMA2 / FMUL2 (packed FP32), UTMALDG / UTMASTG (TMA tile copies through tensor
+maps), UBLKCP (TMA bulk copies), LDGSTS (cp.async).
 python tools/sass_opcodes.py > profiles/r02_sass_opcodes.txt"""
 import collections
 import os
@@ -20,13 +21,13 @@ for line in out.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m and name:
         op = m.group(1)
-        op = ".".join(op.split(".")[:2]) if op.startswith(("LDS", "STS", "LDG", "STG", "SHFL", "MUFU", "LDGSTS", "UBLKCP", "DMMA")) else op.split(".")[0]
+        op = ".".join(op.split(".")[:2]) if op.startswith(("LDS", "STS", "LDG", "STG", "SHFL", "MUFU", "LDGSTS", "UBLKCP", "UTMALDG", "UTMASTG", "DMMA")) else op.split(".")[0]
         counts[name][op] += 1
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
 for n, c in counts.items():
     if not any(h in n for h in HOT):
         continue
     tot = sum(c.values())
-    key = {k: c[k] for k in ("DMMA.8", "DFMA", "FFMA2", "FMUL2", "UBLKCP", "UBLKCP.S", "LDGSTS.E", "LDGSTS", "SYNCS", "FSEL", "MOV", "IMAD") if c.get(k)}
+    key = {k: c[k] for k in ("DMMA.8", "DFMA", "FFMA2", "FMUL2", "UTMALDG.2D", "UTMASTG.2D", "UBLKCP", "UBLKCP.S", "LDGSTS.E", "LDGSTS", "SYNCS", "FSEL", "MOV", "IMAD") if c.get(k)}
     print("== %s\n   %d instructions; %s" % (demangle(n)[:150], tot, ", ".join("%s %d" % kv for kv in key.items())))
     print("   top: " + ", ".join("%s %d" % kv for kv in c.most_common(10)))
