@@ -23,7 +23,13 @@ struct Reflector { double beta, tau, inv_v0; };
 
 __device__ __forceinline__ Reflector make_reflector(double x0, double sigma) {
   Reflector h;
-  if (sigma == 0.0) {  // nothing below the diagonal: identity, or a sign flip to keep R_kk >= 0
+  // Nothing below the diagonal — exactly, or to working precision (|rest| <= 2^-53 |x0|: then ||x|| == |x0| in double and
+  // the reflector is the identity to 2^-106), or a column that is numerically zero against the prescaled matrix (largest
+  // entry in [1, 2)).  Without the last two cases an exactly rank-deficient matrix drives this into the subnormal range: the
+  // residue left under the diagonal shrinks by 2^-53 per eliminated column, after about ten columns v0 = -sigma / (x0 + ||x||)
+  // is ~1e-160, v0^2 is subnormal with a few bits left, and tau = 2 v0^2 / (sigma + v0^2) makes H non-orthogonal at the 1e-7
+  // level (found by the reference's own suite: qr_test.js "random matrices with zero rows", 48 x 52 of rank 4).
+  if (sigma == 0.0 || sigma <= x0 * x0 * 0x1p-106 || fma(x0, x0, sigma) < 0x1p-900) {  // identity, or a sign flip to keep R_kk >= 0
     h.beta = fabs(x0);
     h.tau = (x0 < 0.0) ? 2.0 : 0.0;
     h.inv_v0 = 0.0;  // rest is all zero anyway
@@ -47,7 +53,7 @@ struct ReflectorS { double beta, tau, inv_v0; };
 __device__ __forceinline__ ReflectorS make_reflector_signed(double x0, double sigma) {
   ReflectorS h;
   const double s = fma(x0, x0, sigma);
-  if (s == 0.0) { h.beta = 0.0; h.tau = 0.0; h.inv_v0 = 0.0; return h; }
+  if (s < 0x1p-900) { h.beta = 0.0; h.tau = 0.0; h.inv_v0 = 0.0; return h; }   // numerically zero against the prescaled matrix
   const double rn = rsqrt(s);
   const double nrm = s * rn;
   h.beta = -copysign(nrm, x0);
@@ -617,7 +623,7 @@ qr_tiny_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __r
       for (int i = j + 1; i < rows; i++) sigma = fma(a[i * cols + j], a[i * cols + j], sigma);
       const double alpha = a[j * cols + j];
       double t = 0.0;
-      if (sigma > 0.0) {
+      if (sigma > 0x1p-900) {   // below: a numerically zero column against the prescaled matrix (subnormal squares lose their bits)
         const double nrm = sqrt(fma(alpha, alpha, sigma));
         const double beta = alpha >= 0.0 ? -nrm : nrm;
         t = (beta - alpha) / beta;
