@@ -264,11 +264,12 @@ gemm_tiled_kernel(const double* __restrict__ A, const double* __restrict__ B, do
 // the edges) through a STAGES-deep ring, so global latency is hidden behind the DMMA stream instead of being
 // exposed at every k-tile.  This is the kernel behind the compute-bound figures (C1 and the large-N probes).
 // ------------------------------------------------------------------------------------------------
-template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16, int KS = 1>
 struct PipeCfg {
   static constexpr int BM = WR * TM * 8, BN = WC * TN * 8, BK = BK_;
   static constexpr int LDA = BK + 4, LDB = BN + 4;
-  static constexpr int THREADS = WR * WC * 32;
+  static constexpr int THREADS = WR * WC * KS * 32;   // KS warp groups share a tile: each takes 1/KS of every k-tile (split-K inside the CTA)
+  static_assert((BK / 4) % KS == 0, "k-steps per tile must divide among the warp groups");
   static constexpr int A_CHUNKS = BM * BK / 2, B_CHUNKS = BK * BN / 2;  // 16-byte chunks per tile
   static constexpr int STAGE_DOUBLES = BM * LDA + BK * LDB;
   static constexpr size_t SMEM = sizeof(double) * STAGES * STAGE_DOUBLES;
@@ -281,16 +282,17 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
-__global__ void __launch_bounds__(WR * WC * 32)
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16, int KS = 1>
+__global__ void __launch_bounds__(WR * WC * KS * 32)
 gemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                  int64_t batch, int I, int K, int J, BatchMap map, int tiles_m, int tiles_n) {
-  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_>;
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_, KS>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, T = Cfg::THREADS;
   extern __shared__ __align__(16) double gemm_smem[];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp_all = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const int kgrp = warp_all / (WR * WC), warp = warp_all % (WR * WC);   // warp group kgrp takes k-steps kgrp*(BK/4/KS) .. of every tile
   const int wr = warp / WC, wc = warp % WC;
 
   int64_t tile = blockIdx.x;
@@ -346,7 +348,8 @@ gemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, dou
     const double* as = gemm_smem + (kt % STAGES) * Cfg::STAGE_DOUBLES + (wr * TM * 8 + g) * LDA + t;
     const double* bs = gemm_smem + (kt % STAGES) * Cfg::STAGE_DOUBLES + BM * LDA + t * LDB + wc * TN * 8 + g;
 #pragma unroll
-    for (int ks = 0; ks < BK / 4; ks++) {
+    for (int kq = 0; kq < BK / 4 / KS; kq++) {
+      const int ks = kgrp * (BK / 4 / KS) + kq;
       double af[TM], bfr[TN];
 #pragma unroll
       for (int i = 0; i < TM; i++) af[i] = as[i * 8 * LDA + ks * 4];
@@ -359,6 +362,31 @@ gemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, dou
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
+  if (KS > 1) {   // the groups' partial tiles meet in shared memory (the ring is idle now); group 0 stores
+    __syncthreads();
+    double* red = gemm_smem + (size_t)(warp * 32 + lane) * (TM * TN * 2);
+    for (int gq = KS - 1; gq > 0; gq--) {
+      if (kgrp == gq) {
+#pragma unroll
+        for (int i = 0; i < TM; i++)
+#pragma unroll
+          for (int j = 0; j < TN; j++) *reinterpret_cast<double2*>(red + (i * TN + j) * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+      __syncthreads();
+      if (kgrp == 0) {
+#pragma unroll
+        for (int i = 0; i < TM; i++)
+#pragma unroll
+          for (int j = 0; j < TN; j++) {
+            const double2 p = *reinterpret_cast<const double2*>(red + (i * TN + j) * 2);
+            acc[i][j][0] += p.x;
+            acc[i][j][1] += p.y;
+          }
+      }
+      if (gq > 1) __syncthreads();
+    }
+    if (kgrp != 0) return;
+  }
 
 #pragma unroll
   for (int i = 0; i < TM; i++) {
@@ -372,14 +400,14 @@ gemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, dou
   }
 }
 
-template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16>
+template <int WR, int WC, int TM, int TN, int STAGES, int BK_ = 16, int KS = 1>
 static cudaError_t launch_pipe(cudaStream_t s, const double* A, const double* B, double* C,
                                int64_t batch, int I, int K, int J, const BatchMap& map) {
-  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_>;
+  using Cfg = PipeCfg<WR, WC, TM, TN, STAGES, BK_, KS>;
   const int tiles_m = (I + Cfg::BM - 1) / Cfg::BM, tiles_n = (J + Cfg::BN - 1) / Cfg::BN;
   const int64_t grid = batch * tiles_m * tiles_n;
   if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  auto kern = gemm_pipe_kernel<WR, WC, TM, TN, STAGES, BK_>;
+  auto kern = gemm_pipe_kernel<WR, WC, TM, TN, STAGES, BK_, KS>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -832,7 +860,15 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
       // Split-K over a 2- or 4-CTA cluster with a DSMEM reduction (64x64 tiles, 128 / 256 CTAs) was built and measured:
       // 18.9 / 20.9 us — a 64x64 CTA of 4 warps alone on an SM runs its main loop at ~52 % of the DMMA peak.
       const int64_t t6432 = batch * ((I + 63) / 64) * ((J + 31) / 32);
-      if (t6432 < 2LL * sm_count) return launch_bulk_or_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
+      if (t6432 < 2LL * sm_count) {
+        // split-K inside the CTA: two (or four) warp groups share the 32x32 tile and each takes half (a quarter) of every k-tile,
+        // so that a sub-partition holds 2-4 warps per resident CTA instead of one (ND4B_GEMM_KS=0|1|2|3 for A/B timing)
+        static const int ks_mode = [] { const char* e = getenv("ND4B_GEMM_KS"); return e ? atoi(e) : 0; }();
+        if (ks_mode == 1) return launch_pipe<2, 2, 2, 2, 4, 16, 2>(s, A, B, C, batch, I, K, J, map);
+        if (ks_mode == 2) return launch_pipe<2, 2, 2, 2, 3, 32, 2>(s, A, B, C, batch, I, K, J, map);
+        if (ks_mode == 3) return launch_pipe<2, 2, 2, 2, 3, 32, 4>(s, A, B, C, batch, I, K, J, map);
+        return launch_bulk_or_pipe<2, 2, 2, 2, 4>(s, A, B, C, batch, I, K, J, map);
+      }
       return launch_bulk_or_pipe<4, 1, 2, 4, 4>(s, A, B, C, batch, I, K, J, map);
     }
   }

@@ -342,13 +342,15 @@ __device__ __forceinline__ void qb_store_r(const double (&a)[4][8][2], double* _
   }
 }
 
-template <int P, bool REREAD, bool PADDED>
+template <int P, bool REREAD, bool PADDED, bool LOCK = false>
 __device__ __forceinline__ void qb_r_phase(double (&a)[4][8][2], double* vs, double* ts,
                                            double* __restrict__ r_out, int lane, int g, int t, double post, unsigned& sgn_p,
                                            long long& qb_tm, int L, int cols) {
   double tau_q;
   Acc Gu;
+  if (LOCK) __syncthreads();   // every warp of the SM enters the panel together (no DMMA stream beside a panel chain)
   qb_panel<P, REREAD>(a, vs + kXsOff, lane, g, t, tau_q, sgn_p, Gu);
+  if (LOCK) __syncthreads();
   QB_MARK(2);
   const unsigned s0 = __shfl_sync(kFull, sgn_p, 4 * (2 * t)), s1 = __shfl_sync(kFull, sgn_p, 4 * (2 * t + 1));
   // R: diagonal block and the zero blocks left of it; then the head of the panel becomes the clean unit-lower V
@@ -406,15 +408,16 @@ __device__ __forceinline__ void qb_q_phase(double (&a)[4][8][2], const double* v
 // PADDED: any rows <= 64, cols <= 32: the matrix is zero-padded into the 64 x 32 register tile on load (zero rows leave the
 // reflectors unchanged, zero columns give identity reflectors after the last real column), and only the rows x L block
 // of Q and the L x cols block of R are stored.
-template <int WARPS, int MINB, bool REREAD, bool PADDED, bool TMAP>
+template <int WARPS, int MINB, bool REREAD, bool PADDED, bool TMAP, bool LOCK = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, int64_t batch,
                        int rows, int cols, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_q) {
   extern __shared__ __align__(16) double qb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int64_t m = (int64_t)blockIdx.x * WARPS + warp;
-  if (m >= batch) return;  // warp-uniform; the kernel has no block-level barriers
+  int64_t m = (int64_t)blockIdx.x * WARPS + warp;
+  if (LOCK) { if (m >= batch) m = batch - 1; }   // phase-locked variant: surplus warps redo the last matrix (same bits, benign) to keep the barriers whole
+  else if (m >= batch) return;  // warp-uniform; no block-level barriers
   double* vs;
   if (TMAP) {  // 1 KiB-aligned warp regions (SWIZZLE_128B); the launch adds 1 KiB of slack
     const unsigned base = smem_u32(qb_smem), pad = (1024u - (base & 1023u)) & 1023u;
@@ -502,10 +505,10 @@ qr64x32_blocked_kernel(const double* __restrict__ A, double* __restrict__ Q, dou
   double* r_out = R + m * (PADDED ? L * cols : 1024);
   unsigned sgn[4];
   QB_MARK(0);
-  qb_r_phase<0, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm, L, cols);
-  qb_r_phase<1, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm, L, cols);
-  qb_r_phase<2, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm, L, cols);
-  qb_r_phase<3, REREAD, PADDED>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm, L, cols);
+  qb_r_phase<0, REREAD, PADDED, LOCK>(a, vs, ts, r_out, lane, g, t, post, sgn[0], qb_tm, L, cols);
+  qb_r_phase<1, REREAD, PADDED, LOCK>(a, vs, ts, r_out, lane, g, t, post, sgn[1], qb_tm, L, cols);
+  qb_r_phase<2, REREAD, PADDED, LOCK>(a, vs, ts, r_out, lane, g, t, post, sgn[2], qb_tm, L, cols);
+  qb_r_phase<3, REREAD, PADDED, LOCK>(a, vs, ts, r_out, lane, g, t, post, sgn[3], qb_tm, L, cols);
 
   qb_q_phase<3>(a, vs, ts, lane, g, t);
   qb_q_phase<2>(a, vs, ts, lane, g, t);
@@ -697,7 +700,7 @@ static bool qb_encode_map(CUtensorMap* tm, const void* base, int64_t batch) {
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int WARPS, int MINB, bool REREAD, bool PADDED, bool TMAP = false>
+template <int WARPS, int MINB, bool REREAD, bool PADDED, bool TMAP = false, bool LOCK = false>
 static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double* R, int64_t batch, int rows, int cols,
                              const CUtensorMap* tm_a = nullptr, const CUtensorMap* tm_q = nullptr) {
   static bool attr_set[64] = {false};
@@ -705,12 +708,12 @@ static cudaError_t qb_launch(cudaStream_t s, const double* A, double* Q, double*
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED, TMAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED, TMAP, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   static const CUtensorMap none{};
-  qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED, TMAP><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(
+  qr64x32_blocked_kernel<WARPS, MINB, REREAD, PADDED, TMAP, LOCK><<<(unsigned)((batch + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(
       A, Q, R, batch, rows, cols, tm_a ? *tm_a : none, tm_q ? *tm_q : none);
   return cudaGetLastError();
 }
@@ -726,8 +729,11 @@ cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, d
   const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;
   if (want_tmap && aligned && batch * 64 < 0x7fffffffLL) {
     CUtensorMap tm_a, tm_q;
-    if (qb_encode_map(&tm_a, A, batch) && qb_encode_map(&tm_q, Q, batch))
+    if (qb_encode_map(&tm_a, A, batch) && qb_encode_map(&tm_q, Q, batch)) {
+      // variant 3 (A/B): one CTA of 12 warps per SM, CTA-wide barriers around every panel — no DMMA stream beside a panel chain
+      if (variant == 3) return qb_launch<12, 1, true, false, true, true>(s, A, Q, R, batch, 64, 32, &tm_a, &tm_q);
       return qb_launch<4, 3, true, false, true>(s, A, Q, R, batch, 64, 32, &tm_a, &tm_q);
+    }
   }
   return qb_launch<4, 3, true, false>(s, A, Q, R, batch, 64, 32);
 }
