@@ -732,7 +732,9 @@ cudaError_t launch_qr64x32_blocked(cudaStream_t s, const double* A, double* Q, d
     if (qb_encode_map(&tm_a, A, batch) && qb_encode_map(&tm_q, Q, batch)) {
       // variant 3 (A/B): one CTA of 12 warps per SM, CTA-wide barriers around every panel — no DMMA stream beside a panel chain
       if (variant == 3) return qb_launch<12, 1, true, false, true, true>(s, A, Q, R, batch, 64, 32, &tm_a, &tm_q);
-      return qb_launch<4, 3, true, false, true>(s, A, Q, R, batch, 64, 32, &tm_a, &tm_q);
+      // CTAs of 2 warps, 6 per SM: a finished matrix frees its slot sooner (measured: 1 warp per CTA 1.071 ms, 2: 1.034, 3: 1.090 —
+      // three warps leave a sub-partition short —, 4: 1.046, 6: 1.063)
+      return qb_launch<2, 6, true, false, true>(s, A, Q, R, batch, 64, 32, &tm_a, &tm_q);
     }
   }
   return qb_launch<4, 3, true, false>(s, A, Q, R, batch, 64, 32);
