@@ -67,7 +67,7 @@ NCU_TRAFFIC_BYTES = {
     "c2": (1.578e9, "profiles/r02_ncu_c2.txt"),
     "c3": (1.015e9, "profiles/r02_ncu_c3.txt"),
     "g4k": (1.225e9, "profiles/r02_ncu_g4k_bulk.txt"),
-    "c4": (3.018e9, "profiles/r02_ncu_c4_tmap.txt"),   # 2.68e9 algorithmic + the idle column blocks parked in local memory around the panels
+    "c4": (3.016e9, "profiles/r02_ncu_c4_tmap.txt"),   # 2.68e9 algorithmic + the idle column blocks parked in local memory around the panels
     # three launches per call: FP32 Jacobi 0.777 GB, hand-over 1.825 GB, FP64 Jacobi 2.154 GB (V0, G1, V1 pass through HBM)
     "c5": (4.756e9, "profiles/r02_ncu_c5_pipeline_v2.txt"),
 }
