@@ -14,6 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 #include <functional>
 #include <map>
 #include <unordered_map>
@@ -69,6 +72,7 @@ constexpr int kMaxBuf = kWorkBuf + 1;  // device buffers per slot: up to 3 input
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaEvent_t h2d_done = nullptr;   // recorded after the H2D copies of the chunk in flight: the pinned input ring may be refilled then
   void* buf[kMaxBuf] = {nullptr};
   size_t cap[kMaxBuf] = {0};
   // pinned staging ring for pageable caller memory: [0..2] inputs, [3..5] outputs
@@ -78,6 +82,35 @@ struct Slot {
   struct Pending { double* dst; const void* src; size_t bytes; } pending[3];
   int n_pending = 0;
 };
+
+// Host-to-host copy with non-temporal stores (SSE2, baseline x86-64).  The staging copies move gigabytes that the CPU does not
+// read again (pinned ring -> DMA engine, pinned ring -> caller's result array): ordinary stores first read every destination
+// line into the cache (read-for-ownership), i.e. three bytes of DRAM traffic per byte copied, on a host whose memory bandwidth is
+// what the pageable path is bound by (the copy threads and the two DMA directions share it); streaming stores make it two.
+static void copy_stream(void* dst, const void* src, size_t bytes) {
+#if defined(__x86_64__) || defined(_M_X64)
+  if (bytes < (size_t)1 << 16) { memcpy(dst, src, bytes); return; }
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  const size_t head = (64 - (reinterpret_cast<uintptr_t>(d) & 63)) & 63;   // up to the first 64-byte line of the destination
+  if (head) { memcpy(d, s, head); d += head; s += head; bytes -= head; }
+  const size_t lines = bytes / 64;
+  for (size_t i = 0; i < lines; i++, d += 64, s += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32));
+    const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+  }
+  _mm_sfence();   // the streamed lines are globally visible before the copy is reported done (the DMA reads them next)
+  if (bytes & 63) memcpy(d, s, bytes & 63);
+#else
+  memcpy(dst, src, bytes);
+#endif
+}
 
 // A handful of helper threads that split large host-to-host copies (caller memory <-> pinned ring):
 // one core moves ~10 GB/s, PCIe Gen5 wants ~55 GB/s.
@@ -93,7 +126,7 @@ class CopyPool {
   }
   void copy(void* dst, const void* src, size_t bytes) {
     const size_t parts = std::min<size_t>(workers_.size() + 1, std::max<size_t>(1, bytes >> 20));
-    if (parts <= 1) { memcpy(dst, src, bytes); return; }
+    if (parts <= 1) { copy_stream(dst, src, bytes); return; }
     const size_t step = ((bytes / parts) + 63) & ~size_t(63);
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -105,7 +138,7 @@ class CopyPool {
       }
     }
     cv_.notify_all();
-    memcpy(dst, src, std::min(step, bytes));  // the calling thread takes the first part
+    copy_stream(dst, src, std::min(step, bytes));  // the calling thread takes the first part
     std::unique_lock<std::mutex> lk(mu_);
     done_.wait(lk, [this] { return outstanding_ == 0; });
   }
@@ -122,7 +155,7 @@ class CopyPool {
         t = tasks_.back();
         tasks_.pop_back();
       }
-      memcpy(t.dst, t.src, t.bytes);
+      copy_stream(t.dst, t.src, t.bytes);
       {
         std::lock_guard<std::mutex> lk(mu_);
         if (--outstanding_ == 0) done_.notify_all();
@@ -289,7 +322,10 @@ int init_locked(const int* devices, int n) {
     CU(cudaGetDeviceProperties(&prop, id));
     if (prop.major != 10) { delete c; return fail(ND4B_E_CUDA, "nd4b: device %d is sm_%d%d; this build targets sm_100a (B200) only", id, prop.major, prop.minor); }
     d.sm_count = prop.multiProcessorCount;
-    for (auto& s : d.slots) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (auto& s : d.slots) {
+      CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+    }
     CU(cudaMalloc(&d.d_info, sizeof(long long)));
     CU(cudaMalloc(&d.d_ints, 4 * sizeof(int)));
     c->devs.push_back(d);
@@ -378,7 +414,7 @@ int run_pipeline_body(Context* ctx, int64_t units, const std::vector<Stream1>& i
   if (any_pageable && !ctx->pool) {
     int n = (int)std::thread::hardware_concurrency() / 2 - 1;
     if (const char* e = getenv("ND4B_COPY_THREADS")) n = atoi(e) - 1;
-    ctx->pool = new CopyPool(std::max(0, std::min(n, 7)));
+    ctx->pool = new CopyPool(std::max(0, std::min(n, getenv("ND4B_COPY_THREADS") ? 31 : 7)));
   }
 
   for (auto& dv : ctx->devs)
@@ -415,7 +451,8 @@ int run_pipeline_body(Context* ctx, int64_t units, const std::vector<Stream1>& i
         const void* src = ins[i].in + sh.next * ins[i].elems;
         if (!in_pinned[i]) {  // pageable caller memory: stage through the slot's pinned buffer
           { Timer t(&ctx->t_alloc); if (int rc = ensure_pinned(slot, (int)i, bytes)) return rc; }
-          { Timer t(&ctx->t_wait); CU(cudaStreamSynchronize(slot.stream)); }  // the previous H2D out of this pinned buffer has finished
+          // the previous H2D out of this pinned buffer has finished (its kernel and D2H may still be running: an event, not the stream)
+          { Timer t(&ctx->t_wait); CU(cudaEventSynchronize(slot.h2d_done)); }
           { Timer t(&ctx->t_copy); ctx->pool->copy(slot.pin[i], src, bytes); }
           src = slot.pin[i];
           ctx->staged += bytes;
@@ -429,6 +466,7 @@ int run_pipeline_body(Context* ctx, int64_t units, const std::vector<Stream1>& i
         if (int rc = ensure(slot, kOutBase + (int)i, bytes)) return rc;
         a.out[i] = static_cast<double*>(slot.buf[kOutBase + i]);
       }
+      if (any_pageable) CU(cudaEventRecord(slot.h2d_done, slot.stream));
       a.work = nullptr;
       a.work_bytes = 0;
       if (work_bytes_per_unit) {
@@ -580,6 +618,7 @@ int nd4b_shutdown(void) {
     cudaSetDevice(d.id);
     for (auto& s : d.slots) {
       if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+      if (s.h2d_done) cudaEventDestroy(s.h2d_done);
       for (auto& b : s.buf) if (b) cudaFree(b);
       for (auto& b : s.pin) if (b) cudaFreeHost(b);
     }
