@@ -87,3 +87,24 @@ def test_restated_suite_generators_produce_the_references_items(eng):
             assert np.array_equal(got.view(np.uint64), np.ascontiguousarray(a).view(np.uint64)), (name, k)
         seen += 1
     assert seen == len(want)
+
+
+def test_npy_wire_format_both_ways_against_the_live_reference(eng):
+    """nd4js_b200.io against src/io/npy.js running in the engine: bytes written here are read there and vice versa."""
+    from nd4js_b200 import io
+    from nd4js_b200.nd_array import from_numpy
+    npy = eng.module("io/npy.js")
+    nda = eng.module("nd_array.js")
+    rng = np.random.default_rng(3)
+    for shape in [(3, 4), (2, 3, 5), (7,), (1, 1, 1), (2, 16, 16), (5, 1)]:
+        a = rng.standard_normal(shape)
+        js_bytes = bytes(eng.call("%s.npy_serialize(%s)" % (npy, qjs.js_nd(nda, a))).tolist())
+        ours = bytes(io.npy_serialize(from_numpy(a)))
+        assert ours == js_bytes, shape                                     # byte for byte the reference's file
+        back = io.npy_deserialize(js_bytes)
+        assert tuple(back.shape) == shape and np.array_equal(np.asarray(back.data).reshape(shape), a)
+        got = eng.call("%s.npy_deserialize(__from_hex('%s', Uint8Array))" % (npy, ours.hex()))
+        assert got.shape == shape and np.array_equal(got.view(np.uint64), a.view(np.uint64))
+    i32 = np.arange(-6, 6, dtype=np.int32).reshape(3, 4)
+    js_bytes = bytes(eng.call("%s.npy_serialize(new %s.NDArray(Int32Array.of(3,4), Int32Array.from([%s])))" % (npy, nda, ",".join(map(str, i32.ravel())))).tolist())
+    assert bytes(io.npy_serialize(from_numpy(i32))) == js_bytes
