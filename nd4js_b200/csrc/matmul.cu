@@ -99,6 +99,75 @@ matmul32_kernel(const double* __restrict__ A, const double* __restrict__ B, doub
   }
 }
 
+// The broadcast form of the same product ([batch,32,32] x [1,32,32]): every unit multiplies by the SAME B.  The kernel
+// above would fetch B's fragments again for every matrix (8 KiB per unit through L1 / L2 beside the 8 KiB of A from HBM); here a
+// warp loads them once and keeps them in registers for MPW consecutive matrices, the A fragments of the next matrix in flight
+// while the current one is multiplied.  Same fragment layout, same accumulation order: bit-identical results.
+template <int MPW, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+matmul32_bcast_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                      int64_t batch, BatchMap map) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t m0 = ((int64_t)blockIdx.x * WARPS + warp) * MPW;
+  if (m0 >= batch) return;
+  int64_t ao, bo;
+  decode_batch(map, m0, ao, bo);
+  const double* b = B + bo + (2 * t) * 32 + 2 * g;
+  double2 bf[4][2][2];
+#pragma unroll
+  for (int w = 0; w < 4; w++)
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int x = 0; x < 2; x++) bf[w][h][x] = ldg2(b + (8 * w + h) * 32 + 16 * x);
+
+  // the row block just multiplied is refilled from the next matrix at once: sixteen 16-byte loads per lane stay in flight
+  // without a second set of registers
+  double2 af[4][4];
+  const double* a = A + m0 * map.a_lin + g * 32 + 2 * t;
+#pragma unroll
+  for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+    for (int w = 0; w < 4; w++) af[rb][w] = ldg2_stream(a + rb * 256 + 8 * w);
+#pragma unroll
+  for (int i = 0; i < MPW; i++) {
+    const int64_t m = m0 + i;
+    if (m >= batch) break;   // warp-uniform
+    const bool more = (i + 1 < MPW) && (m + 1 < batch);
+    double* c = C + m * 1024 + g * 32 + 4 * t;
+#pragma unroll
+    for (int rb = 0; rb < 4; rb++) {
+      double acc[2][2][2];
+#pragma unroll
+      for (int x = 0; x < 2; x++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) acc[x][e][0] = acc[x][e][1] = 0.0;
+#pragma unroll
+      for (int w = 0; w < 4; w++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const double av = h ? af[rb][w].y : af[rb][w].x;
+#pragma unroll
+          for (int x = 0; x < 2; x++) {
+            dmma884(acc[x][0][0], acc[x][0][1], av, bf[w][h][x].x);
+            dmma884(acc[x][1][0], acc[x][1][1], av, bf[w][h][x].y);
+          }
+        }
+      if (more) {
+#pragma unroll
+        for (int w = 0; w < 4; w++) af[rb][w] = ldg2_stream(a + (i + 1) * map.a_lin + rb * 256 + 8 * w);
+      }
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        double* p = c + rb * 256 + 16 * x;
+        stg2_stream(p, acc[x][0][0], acc[x][1][0]);
+        stg2_stream(p + 2, acc[x][0][1], acc[x][1][1]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // General tiled GEMM.  CTA = WR x WC warps, each warp owns a (8*TM) x (8*TN) block of C.
 // smem tiles are padded so that DMMA fragment reads (8 rows x 4 k, resp. 4 k x 8 cols of doubles)
@@ -830,6 +899,14 @@ cudaError_t launch_matmul(cudaStream_t s, const double* A, const double* B, doub
   if (I == 32 && K == 32 && J == 32 && aligned && str_even) {
     const int64_t grid = (batch + kMM32Warps - 1) / kMM32Warps;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    // one B for every unit (and A walked linearly): B's fragments stay in registers over four matrices per warp
+    static const bool bcast_on = [] { const char* e = getenv("ND4B_MM32_BCAST"); return !(e && e[0] == '0'); }();
+    if (bcast_on && map.b_lin == 0 && map.a_lin == 1024 && batch >= 4096) {
+      constexpr int MPW = 4, W = 4;
+      const int64_t g4 = (batch + (int64_t)W * MPW - 1) / ((int64_t)W * MPW);
+      matmul32_bcast_kernel<MPW, W, 3><<<(unsigned)g4, W * 32, 0, s>>>(A, B, C, batch, map);
+      return cudaGetLastError();
+    }
     matmul32_kernel<<<(unsigned)grid, kMM32Warps * 32, 0, s>>>(A, B, C, batch, map);
     return cudaGetLastError();
   }
