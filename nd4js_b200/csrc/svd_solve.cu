@@ -52,13 +52,20 @@ svd_lstsq_kernel(const double* __restrict__ U, const double* __restrict__ SV, co
   const double* y = Y + decode1(map, 3, m);
   double* x = X + m * (int64_t)I * J;
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    bool bad = false;
-    s_rank = svd_rank_of(sv, M, &bad);
-    s_bad = bad ? 1 : 0;
+  // The rank cut (svd_rank_of: the first r with |sv_r| <= sqrt(eps) |sv_0|, a non-finite entry before it is an error) found by
+  // all threads at once: one thread walking sv left the rest of the CTA waiting behind 64 dependent global loads.
+  if (tid == 0) { s_rank = M; s_bad = M; }
+  __syncthreads();
+  {
+    const double T0 = mul_rn(kSqrtEps, fabs(sv[0]));
+    for (int r = tid; r < M; r += T) {
+      const double a = fabs(sv[r]);
+      if (!(a <= 1.7976931348623157e308)) atomicMin(&s_bad, r);   // NaN or Infinity
+      else if (a <= T0) atomicMin(&s_rank, r);
+    }
   }
   __syncthreads();
-  if (s_bad) {   // svd.js:168-169: the call throws; nothing of this matrix is defined
+  if (s_bad < s_rank) {   // svd.js:168-169: the scan meets a non-finite value before the cut: the call throws; nothing of this matrix is defined
     if (tid == 0 && fail) atomicExch(fail, 1);
     return;
   }
