@@ -211,12 +211,21 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
           rem.di = __shfl_xor_sync(kFull, back.di, 4 * msk);
           if (lower) cb = rem; else ca = rem;
           __syncwarp();
+          #ifndef PRE32_WCS4
+          if ((lane & 2) == 0) reinterpret_cast<float*>(wcs)[2 * grp + (lane & 1)] = (lane & 1) ? mult.z : mult.x;   // (-alpha, beta): 8 bytes per group, read back with uniform 8-byte loads and duplicated in registers — half the shared-memory wavefronts of the (-alpha, -alpha, beta, beta) form, which was the largest share of this kernel's LSU traffic (C5 15.82 -> 15.23 ms; -DPRE32_WCS4 for A/B)
+#else
           reinterpret_cast<float*>(wcs)[lane] = (lane & 2) ? mult.z : mult.x;   // (-alpha, -alpha, beta, beta) of group grp: one 128-byte wavefront
+#endif
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; j++) {
+#ifndef PRE32_WCS4
+            const float2 ab2 = reinterpret_cast<const float2*>(wcs)[j];
+            const u64 na2 = pack2(ab2.x, ab2.x), b2 = pack2(ab2.y, ab2.y);
+#else
             const float4 ab = wcs[j];
             const u64 na2 = pack2(ab.x, ab.y), b2 = pack2(ab.z, ab.w);
+#endif
             if (j < (j ^ msk)) { rot2(ga[j], ga[j ^ msk], na2, b2); rot2(va[j], va[j ^ msk], na2, b2); }
             else { rot2(gb[j ^ msk], gb[j], na2, b2); rot2(vb[j ^ msk], vb[j], na2, b2); }
           }
@@ -235,12 +244,21 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
         cb.d = __shfl_sync(kFull, cb.d, next_grp_lane);
         cb.di = __shfl_sync(kFull, cb.di, next_grp_lane);
         __syncwarp();
-        reinterpret_cast<float*>(wcs)[lane] = (lane & 2) ? mult.z : mult.x;   // (-alpha, -alpha, beta, beta) of group grp: one 128-byte wavefront
+        #ifndef PRE32_WCS4
+          if ((lane & 2) == 0) reinterpret_cast<float*>(wcs)[2 * grp + (lane & 1)] = (lane & 1) ? mult.z : mult.x;   // (-alpha, beta): 8 bytes per group, read back with uniform 8-byte loads and duplicated in registers — half the shared-memory wavefronts of the (-alpha, -alpha, beta, beta) form, which was the largest share of this kernel's LSU traffic (C5 15.82 -> 15.23 ms; -DPRE32_WCS4 for A/B)
+#else
+          reinterpret_cast<float*>(wcs)[lane] = (lane & 2) ? mult.z : mult.x;   // (-alpha, -alpha, beta, beta) of group grp: one 128-byte wavefront
+#endif
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; i++) {
+#ifndef PRE32_WCS4
+          const float2 ab2 = reinterpret_cast<const float2*>(wcs)[i];
+          const u64 na2 = pack2(ab2.x, ab2.x), b2 = pack2(ab2.y, ab2.y);
+#else
           const float4 ab = wcs[i];
           const u64 na2 = pack2(ab.x, ab.y), b2 = pack2(ab.z, ab.w);
+#endif
           rot2(ga[i], gb[(i + s) & 7], na2, b2);
           rot2(va[i], vb[(i + s) & 7], na2, b2);
         }
