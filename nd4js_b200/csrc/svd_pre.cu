@@ -275,33 +275,39 @@ svd64_pre32_kernel(const double* __restrict__ A, float* __restrict__ V0, int64_t
         gb[i] = mul2(gb[i], db2); vb[i] = mul2(vb[i], db2);
       }
       ca.d = ca.di = cb.d = cb.di = 1.f;
-      // the blocks move one position on: position 0 (warp 0's A) stays, 1 -> 2 -> ... -> 7 -> 1, warp w holding positions w (A)
-      // and 7 - w (B).  New A of warp 1 = old B of warp 0, of warps 2, 3 = old A of the warp before; new B of warps 0..2 =
-      // old B of the next warp, of warp 3 = its own old A.
+      // Next round's partners.  The eight blocks play a round-robin tournament (circle method), but WHICH WARP hosts a pair is
+      // free, and for any two consecutive rounds the hosts can be chosen so that every warp keeps one of its two blocks in its
+      // slot and only swaps the other: after even rounds warps 0, 2 send their B block and warps 1, 3 their A block around the
+      // cycle w1.A -> w0.B -> w2.B -> w3.A -> w1.A, after odd rounds warp 2 sends A and the others B around
+      // w2.A -> w0.B -> w1.B -> w3.B -> w2.A; seven rounds of this (and the same again for the next sweep, from wherever the
+      // blocks then are) meet every pair of blocks exactly once.  Half the shared-memory traffic of moving every block one
+      // position on (which sent 2 and fetched 2 blocks per warp), and with the buffer alternating by round parity one barrier.
       {
-        u64* mine = xbuf + warp * (2 * 16 * 32);
+        const bool odd = (round & 1) != 0;
+        const bool send_a = odd ? (warp == 2) : ((warp & 1) != 0);
+        const int src = odd ? ((0x1302 >> (4 * warp)) & 3) : ((0x2031 >> (4 * warp)) & 3);   // E: 1,3,0,2   O: 2,0,3,1
+        u64* mine = xbuf + (round & 1) * (4 * 16 * 32) + warp * (16 * 32);
+        float* nb = nbuf + (round & 1) * 32;
+        if (send_a) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          mine[i * 32 + lane] = ga[i]; mine[(8 + i) * 32 + lane] = va[i];
-          mine[(16 + i) * 32 + lane] = gb[i]; mine[(24 + i) * 32 + lane] = vb[i];
-        }
-        if ((lane & 3) == 0) { nbuf[warp * 16 + grp] = ca.n; nbuf[warp * 16 + 8 + grp] = cb.n; }
-        __syncthreads();
-        if (warp > 0) {
-          const int sw = warp - 1, sb = (warp == 1) ? 1 : 0;
-          const u64* src = xbuf + sw * (2 * 16 * 32) + sb * (16 * 32);
+          for (int i = 0; i < 8; i++) { mine[i * 32 + lane] = ga[i]; mine[(8 + i) * 32 + lane] = va[i]; }
+          if ((lane & 3) == 0) nb[warp * 8 + grp] = ca.n;
+        } else {
 #pragma unroll
-          for (int i = 0; i < 8; i++) { ga[i] = src[i * 32 + lane]; va[i] = src[(8 + i) * 32 + lane]; }
-          ca.n = nbuf[sw * 16 + sb * 8 + grp];
-        }
-        {
-          const int sw = (warp < 3) ? warp + 1 : 3, sb = (warp < 3) ? 1 : 0;
-          const u64* src = xbuf + sw * (2 * 16 * 32) + sb * (16 * 32);
-#pragma unroll
-          for (int i = 0; i < 8; i++) { gb[i] = src[i * 32 + lane]; vb[i] = src[(8 + i) * 32 + lane]; }
-          cb.n = nbuf[sw * 16 + sb * 8 + grp];
+          for (int i = 0; i < 8; i++) { mine[i * 32 + lane] = gb[i]; mine[(8 + i) * 32 + lane] = vb[i]; }
+          if ((lane & 3) == 0) nb[warp * 8 + grp] = cb.n;
         }
         __syncthreads();
+        const u64* in = xbuf + (round & 1) * (4 * 16 * 32) + src * (16 * 32);
+        if (send_a) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) { ga[i] = in[i * 32 + lane]; va[i] = in[(8 + i) * 32 + lane]; }
+          ca.n = nb[src * 8 + grp];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; i++) { gb[i] = in[i * 32 + lane]; vb[i] = in[(8 + i) * 32 + lane]; }
+          cb.n = nb[src * 8 + grp];
+        }
       }
     }
     more = __syncthreads_or(big) != 0;
