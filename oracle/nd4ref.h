@@ -13,7 +13,7 @@
  * oracle/jsref/gen_golden.py commits its outputs on 81 seeded cases as tests/golden/jsref_golden.npz, and
  * tests/test_jsref_golden.py checks that every function below reproduces them BIT FOR BIT (matmul2, matmul chains,
  * cholesky_decomp incl. the failure texts, tril/triu/cholesky_solve, qr_decomp, qr_decomp_full, _qr_decomp_inplace,
- * qr_lstsq, svd_jac_2sided, svd_rank, svd_lstsq, svd_solve); tests/test_jsref_live.py repeats it on fresh seeds against
+ * qr_lstsq, svd_jac_2sided, svd_rank, svd_lstsq, svd_solve); tests/jsref_live_cases.py repeats it on fresh seeds against
  * the live engine.  The reference's own known answers are checked as well (matmul_test.js:32-78, help.js:1876-1885,
  * _generic_test_svd_decomp.js:180-216) and its property suites with its tolerances.
  * nd.la.svd_jac_1sided does not exist in the reference snapshot: for it PARITY IS UNPINNED by the reference; the
