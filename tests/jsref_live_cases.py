@@ -40,12 +40,12 @@ def test_oracle_bit_identical_with_live_reference(eng, seed):
 
 
 def test_restated_suite_generators_produce_the_references_items(eng):
-    """The first items every spec of _generic_test_svd_decomp.js hands to the SVD under test, recorded from the running
+    """The first 20 items every spec of _generic_test_svd_decomp.js hands to the SVD under test, recorded from the running
     suite, equal the items of tests/ref_suites.py bit for bit (so the GPU tests that consume ref_suites run on the
     reference's own inputs)."""
     import ref_suites as rs
     from oracle.jsref import jasmine
-    K = 8
+    K = 20
     run = jasmine.Runner(eng)
     g = eng.module("la/_generic_test_svd_decomp.js")
     svd = eng.module("la/svd_jac_2sided.js")
